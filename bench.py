@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- SqueezeNet1.0 images/sec on 1/2/4/8 B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+Own arm (default): one process per GPU (torchrun for N>1), batch-sharded, replicated weights, weak scaling
+(every GPU runs `--batch` images per step, default 256 = BASELINE.json configs[2]).  A "step" is one pass of
+the hot path (all 66 nodes) over one batch of synthetic images.
+  value  = images/s with inputs already resident in HBM (CUDA events, barrier + sync both sides, max over ranks)
+  e2e    = images/s through the C-ABI host entry point b200_model_run: pinned host input -> H2D -> run -> D2H
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section 5.
+Reference arm (--impl reference): the reference's CPU algorithm (the oracle restatement; the Rust crate cannot be
+built in this image) on all host threads, on a bounded sample of the same workload; rank 0 only.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SqueezeNet1.0 images/sec"
+SYNTH_MODEL = os.path.join(ROOT, "models", "squeezenet1.0-8-synth.onnx")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "src": "measured"}
+    # fallback stated by B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(images: int, threads: int, seed: int = 11):
+    """Oracle (CPU restatement of the reference algorithm) on `images` synthetic images with `threads` host threads."""
+    import numpy as np
+    from onnx_rusty_inference_engine_b200 import synth
+    from oracle import onnx_wire as ow, ref_model as rm
+    synth.ensure_squeezenet(SYNTH_MODEL, seed=0)
+    model = ow.load_model(SYNTH_MODEL)
+    xs = synth.synthetic_batch(images, seed=seed)
+    t0 = time.perf_counter()
+    out = rm.run_batch(model, xs, threads=threads)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out).all()
+    return images / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    per_step = threads  # one image per host thread per step: a bounded sample of the batch-256 workload
+    cpu_reference_rate(min(2, per_step), min(2, threads))  # builds the oracle .so, warms caches
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_rate(per_step, threads)
+    steps = max(1, min(args.steps, 6))
+    t_total, n_total = 0.0, 0
+    for s in range(steps):
+        _, dt = cpu_reference_rate(per_step, threads, seed=100 + s)
+        t_total += dt; n_total += per_step
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SqueezeNet1.0-8 synthetic 3x224x224 fp32, batch 256 (configs[2])",
+                   "sample": f"{per_step} images per step (1 per host thread), batch-1 reference runs"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_total} images, {threads} threads; C restatement of the reference algorithm "
+                                   "(Rust toolchain absent, oracle/_ref cannot be built)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from onnx_rusty_inference_engine_b200 import _lib, synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+
+    if rank == 0:
+        synth.ensure_squeezenet(SYNTH_MODEL, seed=0)
+    if world > 1:
+        dist.barrier()
+    # a dedicated (non-default) stream shared by torch, NCCL and the backend, so that the CUDA events below
+    # bracket exactly the backend's launches
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng = Engine(SYNTH_MODEL, device=local, stream=stream.cuda_stream)
+    if args.conv_path:
+        eng.model.set_option("conv_path", args.conv_path)
+
+    # synthetic inputs: two distinct resident batches per rank (each 154 MB > the 126 MB L2, and a step streams
+    # gigabytes of activations, so no input or activation survives in L2 between timed steps)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    xs = [torch.randn((B, 3, 224, 224), generator=g, device=dev, dtype=torch.float32) * 10.0 for _ in range(2)]
+    out = torch.empty((B, eng.out_per_image), device=dev, dtype=torch.float32)
+    gathered = torch.empty((world * B, eng.out_per_image), device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step(i):
+        eng.run_torch(xs[i % 2], out)
+        if world > 1:  # the only collective: logits to every rank (8.2 MB at 8 x 256 x 1000)
+            dist.all_gather_into_tensor(gathered, out)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(K):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = eng.ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms / 1e3)
+    assert torch.isfinite(out).all()
+
+    # ---- e2e: the C-ABI host entry point, pinned host buffers, H2D and D2H inside the timed region
+    xh = [torch.randn((B, 3, 224, 224), dtype=torch.float32).mul_(10.0).pin_memory() for _ in range(2)]
+    oh = torch.empty((B, eng.out_per_image), dtype=torch.float32).pin_memory()
+    for i in range(2):
+        eng.run_pinned(xh[i % 2], oh)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        eng.run_pinned(xh[i % 2], oh)   # synchronous: returns when the logits are in host memory
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * Ke / float(te.item())
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- roofline of the dominant kernel family (Conv), timed per launch with CUDA events on the launching
+        # stream inside the library (b200_model_profile), L2 flushed before every timed launch
+        prof = eng.model.profile(B, iters=3, flush_l2=True)
+        conv = [p for p in prof if p["kind"].startswith("conv")]
+        conv_ms = sum(p["ms"] for p in conv)
+        conv_flops = sum(p["flops"] for p in conv)
+        total_ms = sum(p["ms"] for p in prof)
+        top = max(prof, key=lambda p: p["ms"])
+        tensor_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0   # TF32 = bf16/2; 3xTF32 = three MMAs per useful MAC
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        bw = [p for p in prof if not p["kind"].startswith("conv") and not p["kind"].startswith("matmul")]
+        bw_ms = sum(p["ms"] for p in bw)
+        bw_gbs = sum(p["bytes"] for p in bw) / (bw_ms * 1e-3) / 1e9 if bw_ms > 0 else None
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": achieved / tensor_peak, "traffic": None,
+            "kernel": "conv (all 26 Conv launches of one step: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
+            "peak_source": f"{peaks['src']}: bf16_tflops_sustained {peaks['bf16_tflops_sustained']} / 2 (TF32) / 3 (3xTF32)",
+            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / total_ms if total_ms else None,
+            "top_launch": {"name": top["name"], "kind": top["kind"], "ms": top["ms"],
+                           "tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else None},
+            "hbm_ops": {"achieved_gbs": bw_gbs, "peak_gbs": peaks["hbm_gbs"],
+                        "frac": (bw_gbs / peaks["hbm_gbs"]) if bw_gbs else None, "ms_per_step": bw_ms},
+        }
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump(prof, f, indent=1)
+        cpu_line = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            threads = max(1, min(cores, 64))
+            n_img = max(threads, 8)
+            rate, dt = cpu_reference_rate(n_img, threads)
+            cpu_line = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                        "sample": f"{n_img} images of the batch-{B} workload in {dt:.1f} s; C restatement of the "
+                                  "reference algorithm (oracle/ref_ops.c), one batch-1 run per image"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"SqueezeNet1.0-8 (seeded synthetic weights) batch {B} per GPU, 3x224x224 fp32 "
+                                   "N(0,10^2) (BASELINE.json configs[2])",
+                       "global_batch": world * B, "parallelism": f"batch-sharded x{world}, replicated weights",
+                       "l2": "inputs (154 MB per batch, two alternating) and activations exceed the 126 MB L2",
+                       "conv_path": args.conv_path},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
+                    "d2h_bytes_per_step": B * eng.out_per_image * 4, "steps": Ke},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_line,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--conv-path", type=int, default=0, dest="conv_path")
+    ap.add_argument("--profile-out", default=None, dest="profile_out")
+    ap.add_argument("--no-cpu-baseline", action="store_true", dest="no_cpu_baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_own(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

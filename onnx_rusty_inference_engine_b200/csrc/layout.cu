@@ -1,0 +1,139 @@
+// Layout kernels: logical NCHW (what the reference's ndarray holds and what crosses the ABI) <-> the
+// backend's channels-last rows.  All HBM-bound; one coalesced side each, 64-bit indexing.
+#include "internal.h"
+
+namespace b200 {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+  long long b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// dst[n][h][w][0..ld) <- src[n][c][h][w]; thread per (pixel, lane): writes coalesced, reads coalesced per plane.
+__global__ void nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long HW,
+                                    long long pixels, int ld, int lanes /* C or ld (zero-filling) */) {
+  const long long total = pixels * lanes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / lanes;
+    const int c = (int)(i - pix * lanes);
+    const long long n = pix / HW, hw = pix - n * HW;
+    float v = 0.f;
+    if (c < C) v = __ldg(src + (n * C + c) * HW + hw);
+    dst[pix * ld + c] = v;
+  }
+}
+
+// dst[n][c][h][w] <- src rows; thread per output element: writes coalesced.
+__global__ void rows_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long HW,
+                                    long long pixels, int ld) {
+  const long long total = pixels * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    const long long nc = i / HW;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    dst[i] = __ldg(src + (n * HW + hw) * ld + c);
+  }
+}
+
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long pixels,
+                                 int lds, int ldd) {
+  const long long total = pixels * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    dst[pix * ldd + c] = __ldg(src + pix * lds + c);
+  }
+}
+
+__global__ void copy_rows_vec4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int C4,
+                                      long long pixels, int lds4, int ldd4) {
+  const long long total = pixels * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C4;
+    const int c = (int)(i - pix * C4);
+    dst[pix * ldd4 + c] = __ldg(src + pix * lds4 + c);
+  }
+}
+
+__global__ void transpose2d_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(long long)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+__global__ void fill_zero_kernel(float* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = 0.f;
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+int launch_nchw_to_rows(const float* src, TView dst, bool zero_pad_lanes, cudaStream_t st) {
+  const long long pixels = dst.pixels();
+  if (pixels == 0 || dst.C == 0) return 0;
+  const int lanes = zero_pad_lanes ? dst.ld : dst.C;
+  nchw_to_rows_kernel<<<grid_for(pixels * lanes, kThreads), kThreads, 0, st>>>(
+      src, dst.p, dst.C, (long long)dst.H * dst.W, pixels, dst.ld, lanes);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rows_to_nchw(TView src, float* dst, cudaStream_t st) {
+  const long long pixels = src.pixels();
+  if (pixels == 0 || src.C == 0) return 0;
+  rows_to_nchw_kernel<<<grid_for(pixels * src.C, kThreads), kThreads, 0, st>>>(
+      src.p, dst, src.C, (long long)src.H * src.W, pixels, src.ld);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_copy_rows(TView src, TView dst, cudaStream_t st) {
+  const long long pixels = src.pixels();
+  if (pixels == 0 || src.C == 0) return 0;
+  if (src.C % 4 == 0 && src.ld % 4 == 0 && dst.ld % 4 == 0 && aligned16(src.p) && aligned16(dst.p)) {
+    copy_rows_vec4_kernel<<<grid_for(pixels * (src.C / 4), kThreads), kThreads, 0, st>>>(
+        (const float4*)src.p, (float4*)dst.p, src.C / 4, pixels, src.ld / 4, dst.ld / 4);
+  } else {
+    copy_rows_kernel<<<grid_for(pixels * src.C, kThreads), kThreads, 0, st>>>(src.p, dst.p, src.C, pixels,
+                                                                               src.ld, dst.ld);
+  }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_transpose2d(const float* src, int R, int C, float* dst, cudaStream_t st) {
+  if (R == 0 || C == 0) return 0;
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose2d_kernel<<<grid, block, 0, st>>>(src, R, C, dst);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_fill_zero(float* p, size_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  fill_zero_kernel<<<grid_for((long long)n, kThreads), kThreads, 0, st>>>(p, n);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,1042 @@
+// Graph-level executor: the device-resident successor of inference() / node_inference()
+// (src/inference_engine/model_inference.rs:29-162) and of the branch scheduler in
+// src/inference_engine/multithreading/*.rs.
+//
+// What the reference does per inference          What this file does once per (model, batch size)
+//   walk graph.node in file order                  same order, but into a launch plan
+//   re-decode every initializer on every use       weights laid out + uploaded once (utils.rs:113-185)
+//   clone tensors in and out of a HashMap          activations live in one HBM arena; names -> views
+//   Conv, Add([C,1,1]), Relu as three passes       one kernel, Add/Relu in the epilogue
+//   Concat copies both inputs                      producers write at a channel offset of the result
+//   Dropout / Reshape copy                         aliases (Reshape's NCHW order folded into MatMul's weight)
+//   2 worker threads per Fire module               one stream; the plan is replayed as a CUDA graph
+// Results are independent of node scheduling in the reference, so a single in-order stream is faithful.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <set>
+#include <sstream>
+
+#include "internal.h"
+#include "onnx_wire.h"
+
+namespace b200 {
+namespace {
+
+struct DevBuf {
+  float* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct Val {  // one graph value for the planned batch
+  int rank = 0;
+  int64_t dims[4] = {0, 0, 0, 0};  // logical, dims[0] already scaled to the batch
+  TView v;
+  bool planned = false;      // has a device location
+  bool pad_zeroed = false;   // lanes [C, ld) are zero
+  bool is_init = false;      // initializer (constant)
+  const WireTensor* init = nullptr;
+  std::shared_ptr<std::vector<float>> host2d;  // constant rank-2 value produced by Reshape(initializer)
+  // set when this value is a flatten of a channels-last activation whose NCHW order has been
+  // folded into the consumer MatMul's weight: rows are in (h, w, c) order
+  int perm_C = 0, perm_HW = 0;
+};
+
+struct Step {
+  std::string name, kind;
+  double flops = 0, bytes = 0;
+  std::function<int(cudaStream_t)> run;
+};
+
+struct Plan {
+  int64_t batch = 0;
+  std::vector<Step> steps;
+  std::unique_ptr<DevBuf> arena;
+  size_t arena_used = 0;
+  TView in_view;            // where the input transform writes
+  bool in_zero_pad = false;
+  bool in_direct = false;   // input needs no transform (C == 1 or H*W == 1): memcpy
+  float* out_ptr = nullptr; // dense [batch, out_per_image]
+  int64_t out_per_image = 0;
+  bool out_needs_nchw = false;
+  TView out_view;
+  cudaGraphExec_t graph_exec = nullptr;
+  ~Plan() { if (graph_exec) cudaGraphExecDestroy(graph_exec); }
+};
+
+int64_t attr_i(const WireNode& n, const char* name, int64_t dflt) {
+  for (auto& a : n.attr) if (a.name == name) return a.i;
+  return dflt;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_model {
+  b200_ctx* ctx = nullptr;
+  WireModel wm;
+  std::string input_name;
+  int64_t in_dims[4] = {1, 0, 0, 0};  // static dims of the graph input (dims[0] = the model's batch, normally 1)
+  int64_t out_per_image = 0;
+  std::map<std::string, std::unique_ptr<DevBuf>> consts;              // device-resident constants by key
+  std::map<std::string, std::shared_ptr<TcWeights>> tc_weights;       // tcgen05 weight preparations by key
+  std::map<int64_t, std::unique_ptr<Plan>> plans;
+  int opt_cuda_graph = 1;
+  int opt_conv_path = 0;
+  int opt_verbose = 0;
+  float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
+  float* stage_out = nullptr; size_t stage_out_bytes = 0;
+  ~b200_model() {
+    if (stage_in) cudaFree(stage_in);
+    if (stage_out) cudaFree(stage_out);
+  }
+};
+
+namespace b200 {
+namespace {
+
+struct Guard {
+  b200_ctx* c;
+  int prev = -1;
+  explicit Guard(b200_ctx* ctx) : c(ctx) {
+    c->mu.lock();
+    cudaGetDevice(&prev);
+    if (prev != c->device) cudaSetDevice(c->device);
+  }
+  ~Guard() {
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+    c->mu.unlock();
+  }
+};
+
+// ---------------------------------------------------------------- constants
+int upload_const(b200_model* m, const std::string& key, const std::vector<float>& host, float** out) {
+  auto it = m->consts.find(key);
+  if (it != m->consts.end()) { *out = it->second->p; return 0; }
+  std::unique_ptr<DevBuf> b(new DevBuf());
+  b->bytes = std::max<size_t>(host.size() * sizeof(float), 16);
+  if (cudaMalloc((void**)&b->p, b->bytes) != cudaSuccess) B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for constant %s", b->bytes, key.c_str());
+  if (!host.empty()) B200_CUDA(cudaMemcpy(b->p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = b->p;
+  m->consts[key] = std::move(b);
+  return 0;
+}
+
+// Shape of an initializer as the reference sees it: graph.input dims (utils.rs:122) else TensorProto.dims.
+std::vector<int64_t> init_dims(const WireModel& wm, const WireTensor& t) {
+  if (const WireValueInfo* vi = wm.find_input(t.name)) {
+    bool ok = !vi->dims.empty();
+    for (auto d : vi->dims) if (d < 0) ok = false;
+    if (ok) return vi->dims;
+  }
+  return t.dims;
+}
+
+struct Planner {
+  b200_model* m;
+  Plan* plan;
+  int64_t B;
+  std::map<std::string, Val> env;
+  std::map<std::string, int> n_consumers;
+  std::map<std::string, std::pair<std::string, int>> redirect;  // value -> (concat output, channel offset)
+  std::set<size_t> consumed;                                    // node indices folded into an earlier step
+  std::vector<std::pair<size_t, size_t>> arena_allocs;
+
+  // ----- arena: plain bump allocation, 256-byte aligned, sized in a dry pass then materialised
+  size_t arena_cursor = 0;
+  bool dry = true;
+  float* arena_alloc(size_t floats) {
+    size_t bytes = (floats * sizeof(float) + 255) & ~(size_t)255;
+    size_t off = arena_cursor;
+    arena_cursor += bytes;
+    if (dry) return nullptr;
+    return (float*)((char*)plan->arena->p + off);
+  }
+
+  const WireNode* sole_consumer(const std::string& value, size_t* idx) {
+    if (n_consumers[value] != 1) return nullptr;
+    if (!m->wm.outputs.empty() && m->wm.outputs[0].name == value) return nullptr;
+    for (size_t i = 0; i < m->wm.nodes.size(); ++i)
+      for (auto& in : m->wm.nodes[i].input)
+        if (in == value) { *idx = i; return &m->wm.nodes[i]; }
+    return nullptr;
+  }
+
+  Val* get(const std::string& name) {
+    auto it = env.find(name);
+    if (it != env.end()) return &it->second;
+    const WireTensor* t = m->wm.find_initializer(name);
+    if (!t) return nullptr;
+    Val v;
+    v.is_init = true; v.init = t;
+    auto d = init_dims(m->wm, *t);
+    v.rank = (int)d.size();
+    for (int i = 0; i < v.rank && i < 4; ++i) v.dims[i] = d[i];
+    env[name] = v;
+    return &env[name];
+  }
+
+  // Device location for a rank-4 / rank-2 activation about to be produced.
+  int place(const std::string& name, Val* v) {
+    auto r = redirect.find(name);
+    if (v->rank == 4) {
+      v->v.N = (int)v->dims[0]; v->v.C = (int)v->dims[1]; v->v.H = (int)v->dims[2]; v->v.W = (int)v->dims[3];
+      if (r != redirect.end()) {
+        Val* parent = &env[r->second.first];
+        if (!parent->planned) {
+          parent->v.N = (int)parent->dims[0]; parent->v.C = (int)parent->dims[1];
+          parent->v.H = (int)parent->dims[2]; parent->v.W = (int)parent->dims[3];
+          parent->v.ld = parent->v.C;
+          parent->v.p = arena_alloc((size_t)parent->v.pixels() * parent->v.ld);
+          parent->planned = true;
+        }
+        v->v.ld = parent->v.ld;
+        v->v.p = dry ? nullptr : parent->v.p + r->second.second;
+      } else {
+        v->v.ld = v->v.C;
+        v->v.p = arena_alloc((size_t)v->v.pixels() * v->v.ld);
+      }
+    } else {
+      v->v.N = (int)v->dims[0]; v->v.C = (int)v->dims[1]; v->v.H = v->v.W = 1; v->v.ld = v->v.C;
+      v->v.p = arena_alloc((size_t)v->v.numel());
+    }
+    v->planned = true;
+    return 0;
+  }
+
+  void add_step(const std::string& name, const char* kind, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
+    if (dry) return;
+    Step s; s.name = name; s.kind = kind; s.flops = flops; s.bytes = bytes; s.run = std::move(fn);
+    plan->steps.push_back(std::move(s));
+  }
+
+  // ----- weights
+  // Conv weights [M,C,kh,kw] -> device [M][kh][kw][Cp] (K-contiguous rows); Cp > C adds zero lanes.
+  int conv_weights(const WireTensor& w, const std::vector<int64_t>& d, int Cp, float** out) {
+    const int M = (int)d[0], C = (int)d[1], kh = (int)d[2], kw = (int)d[3];
+    std::string key = "convw:" + w.name + ":" + std::to_string(Cp);
+    if (m->consts.count(key)) { *out = m->consts[key]->p; return 0; }
+    if ((int64_t)w.f32.size() != (int64_t)M * C * kh * kw) B200_FAIL(B200_EINVAL, "initializer %s: %zu floats, dims say %lld", w.name.c_str(), w.f32.size(), (long long)M * C * kh * kw);
+    std::vector<float> h((size_t)M * kh * kw * Cp, 0.f);
+    for (int mm = 0; mm < M; ++mm)
+      for (int c = 0; c < C; ++c)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s)
+            h[(((size_t)mm * kh + r) * kw + s) * Cp + c] = w.f32[(((size_t)mm * C + c) * kh + r) * kw + s];
+    return upload_const(m, key, h, out);
+  }
+  int vec_const(const WireTensor& t, size_t expect, float** out) {
+    if (t.f32.size() != expect) B200_FAIL(B200_EINVAL, "initializer %s: %zu floats, expected %zu", t.name.c_str(), t.f32.size(), expect);
+    return upload_const(m, "vec:" + t.name, t.f32, out);
+  }
+
+  // ----- shape pre-pass results are written into env as unplanned Vals
+  int run();
+  int do_conv(size_t i);
+  int do_maxpool(size_t i);
+  int do_relu(size_t i);
+  int do_add(size_t i);
+  int do_matmul(size_t i);
+  int do_reshape(size_t i);
+  int do_concat(size_t i);
+  int do_dropout(size_t i);
+  int do_gap(size_t i);
+  int do_softmax(size_t i);
+  int plan_concat_redirects();
+};
+
+int Planner::plan_concat_redirects() {
+  // A Concat(axis=1) of two rank-4 activations becomes a zero-copy view: each input is produced
+  // directly at its channel offset inside the Concat result.  Needs a shape-only pass first: outputs of
+  // Conv/MaxPool/Relu/... are only known while walking, so the offsets are fixed lazily in do_concat's
+  // counterpart below; here we only decide eligibility (input produced by a node, used by no other Concat).
+  std::map<std::string, int> concat_uses;
+  for (auto& n : m->wm.nodes)
+    if (n.op_type == "Concat")
+      for (auto& in : n.input) concat_uses[in]++;
+  for (auto& n : m->wm.nodes) {
+    if (n.op_type != "Concat" || n.input.size() != 2 || attr_i(n, "axis", 1) != 1) continue;
+    bool ok = n.input[0] != n.input[1];
+    for (auto& in : n.input) {
+      if (concat_uses[in] != 1) ok = false;
+      if (in == m->input_name || m->wm.find_initializer(in)) ok = false;
+      // the producer must be an op that writes its own output buffer (aliases such as Dropout do not)
+      bool producer_ok = false;
+      for (auto& pn : m->wm.nodes)
+        if (!pn.output.empty() && pn.output[0] == in)
+          producer_ok = pn.op_type == "Conv" || pn.op_type == "Relu" || pn.op_type == "MaxPool" || pn.op_type == "Add";
+      if (!producer_ok) ok = false;
+    }
+    if (!ok) continue;
+    // channel offsets are patched once shapes are known (second of the pair set in run())
+    redirect[n.input[0]] = {n.output[0], 0};
+    redirect[n.input[1]] = {n.output[0], -1};
+  }
+  return 0;
+}
+
+static int attr_check(const WireNode& n, std::initializer_list<const char*> allowed, const char* what) {
+  for (auto& a : n.attr) {
+    bool ok = false;
+    for (auto s : allowed) if (a.name == s) ok = true;
+    if (!ok) B200_FAIL(B200_EUNSUPPORTED, "ATTRIBUTE NAME FOR %s NOT FOUND, %s", what, a.name.c_str());
+  }
+  return 0;
+}
+
+static const WireAttr* find_attr(const WireNode& n, const char* name) {
+  for (auto& a : n.attr) if (a.name == name) return &a;
+  return nullptr;
+}
+
+static int parse_conv_attrs(const WireNode& n, b200_conv_params* p) {
+  // convolution(), convolution_op.rs:137-163
+  B200_TRY(attr_check(n, {"auto_pad", "dilations", "group", "kernel_shape", "pads", "strides"}, "CONVOLUTION"));
+  memset(p, 0, sizeof(*p));
+  p->auto_pad = B200_PAD_VALID;  // default, :134
+  if (auto a = find_attr(n, "auto_pad")) {
+    if (a->s == "SAME_UPPER") p->auto_pad = B200_PAD_SAME_UPPER;
+    else if (a->s == "SAME_LOWER") p->auto_pad = B200_PAD_SAME_LOWER;
+    else if (a->s == "VALID") p->auto_pad = B200_PAD_VALID;
+    else if (a->s == "NOT_SET") p->auto_pad = B200_PAD_NOTSET;  // sic, :143
+    else B200_FAIL(B200_EUNSUPPORTED, "Convolution Auto Pad specified not found: %s", a->s.c_str());
+  }
+  if (auto a = find_attr(n, "dilations")) { if (a->ints.size() >= 2) { p->dilations[0] = a->ints[0]; p->dilations[1] = a->ints[1]; } }
+  if (auto a = find_attr(n, "group")) p->group = a->i;
+  if (auto a = find_attr(n, "pads")) { if (a->ints.size() < 4) B200_FAIL(B200_EINVAL, "Conv pads needs 4 ints"); for (int i = 0; i < 4; ++i) p->pads[i] = a->ints[i]; }
+  if (auto a = find_attr(n, "strides")) { if (a->ints.size() >= 2) { p->strides[0] = a->ints[0]; p->strides[1] = a->ints[1]; } }
+  return 0;
+}
+
+static int parse_pool_attrs(const WireNode& n, b200_pool_params* p) {
+  // max_pool(), max_pool_op.rs:88-113
+  B200_TRY(attr_check(n, {"auto_pad", "kernel_shape", "pads", "storage_order", "strides"}, "MAX POOL"));
+  memset(p, 0, sizeof(*p));
+  p->auto_pad = B200_PAD_VALID;
+  if (auto a = find_attr(n, "auto_pad")) {
+    if (a->s == "SAME_UPPER") p->auto_pad = B200_PAD_SAME_UPPER;
+    else if (a->s == "SAME_LOWER") p->auto_pad = B200_PAD_SAME_LOWER;
+    else if (a->s == "VALID") p->auto_pad = B200_PAD_VALID;
+    else if (a->s == "NOTSET") p->auto_pad = B200_PAD_NOTSET;  // sic, :96
+    else B200_FAIL(B200_EUNSUPPORTED, "MaxPool Auto Pad specified not found: %s", a->s.c_str());
+  }
+  if (auto a = find_attr(n, "kernel_shape")) { if (a->ints.size() >= 2) { p->kernel[0] = a->ints[0]; p->kernel[1] = a->ints[1]; } }
+  if (auto a = find_attr(n, "pads")) { if (a->ints.size() >= 4) for (int i = 0; i < 4; ++i) p->pads[i] = a->ints[i]; }
+  if (auto a = find_attr(n, "strides")) { if (a->ints.size() >= 2) { p->strides[0] = a->ints[0]; p->strides[1] = a->ints[1]; } }
+  return 0;
+}
+
+int Planner::do_conv(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  if (n.input.size() < 2 || n.output.empty()) B200_FAIL(B200_EINVAL, "Conv node %s: needs 2 inputs", n.name.c_str());
+  Val* x = get(n.input[0]);
+  Val* w = get(n.input[1]);
+  if (!x || !w) B200_FAIL(B200_EINVAL, "Conv %s: input %s not available", n.name.c_str(), (!x ? n.input[0] : n.input[1]).c_str());
+  if (x->is_init) B200_FAIL(B200_EUNSUPPORTED, "Conv %s: constant data input is not supported by the graph path", n.name.c_str());
+  if (!w->is_init) B200_FAIL(B200_EUNSUPPORTED, "Conv %s: weights must be an initializer", n.name.c_str());
+  if (x->rank != 4 || w->rank != 4) B200_FAIL(B200_EINVAL, "Conv %s: operands must be rank 4 (convolution_op.rs:101,111)", n.name.c_str());
+  b200_conv_params p;
+  B200_TRY(parse_conv_attrs(n, &p));
+  int64_t yd[4];
+  B200_TRY(b200_conv2d_out_dims(x->dims, w->dims, &p, yd));
+  Geo g;
+  {
+    int ap = p.auto_pad;
+    if (p.pads[0] > 0 || p.pads[1] > 0 || p.pads[2] > 0 || p.pads[3] > 0) ap = B200_PAD_NOTSET;
+    B200_TRY(ref_geometry(ap, (int)x->dims[2], (int)x->dims[3], (int)w->dims[2], (int)w->dims[3], (int)p.strides[0], (int)p.strides[1], p.pads, &g));
+  }
+  const int M = (int)w->dims[0], C = (int)w->dims[1], KH = (int)w->dims[2], KW = (int)w->dims[3];
+  const WireTensor* bias = nullptr;
+  if (n.input.size() > 2) {
+    bias = m->wm.find_initializer(n.input[2]);
+    if (!bias) B200_FAIL(B200_EINVAL, "Conv %s: bias %s must be an initializer (convolution_op.rs:124)", n.name.c_str(), n.input[2].c_str());
+  }
+  // ---- epilogue fusion: Conv -> [Add(initializer [M,1,1])] -> [Relu], each link single-consumer
+  std::string out_name = n.output[0];
+  const WireTensor* chan_add = nullptr;
+  int relu = 0;
+  std::string label = n.name.empty() ? n.output[0] : n.name;
+  size_t j;
+  if (const WireNode* c = sole_consumer(out_name, &j)) {
+    if (c->op_type == "Add" && c->input.size() == 2 && c->input[0] == out_name) {
+      const WireTensor* t = m->wm.find_initializer(c->input[1]);
+      if (t) {
+        auto d = init_dims(m->wm, *t);
+        if (d.size() == 3 && d[0] == M && d[1] == 1 && d[2] == 1) {
+          chan_add = t; consumed.insert(j); out_name = c->output[0]; label += "+Add";
+        }
+      }
+    }
+  }
+  if (const WireNode* c = sole_consumer(out_name, &j)) {
+    if (c->op_type == "Relu" && !consumed.count(j)) { relu = 1; consumed.insert(j); out_name = c->output[0]; label += "+Relu"; }
+  }
+  Val y;
+  y.rank = 4; memcpy(y.dims, yd, sizeof(yd));
+  B200_TRY(place(out_name, &y));
+  // ---- operand preparation
+  int Ceff = C;
+  if (C % 4 != 0 && C >= 3 && x->pad_zeroed && x->v.ld == round_up4(C)) Ceff = round_up4(C);
+  float *dw = nullptr, *db = nullptr, *dadd = nullptr;
+  B200_TRY(conv_weights(*w->init, {M, C, KH, KW}, Ceff, &dw));
+  if (bias) B200_TRY(vec_const(*bias, (size_t)M, &db));
+  if (chan_add) B200_TRY(vec_const(*chan_add, (size_t)M, &dadd));
+  ConvArgs a{};
+  a.x = x->v.p; a.N = x->v.N; a.C = Ceff; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
+  a.w = dw; a.M = M; a.KH = KH; a.KW = KW; a.K = KH * KW * Ceff; a.wc = Ceff; a.ldw = a.K;
+  a.bias = db; a.chan_add = dadd;
+  a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
+  a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl; a.relu = relu;
+  const double P = (double)y.v.pixels();
+  const double flops = 2.0 * P * M * C * KH * KW;
+  const double bytes = 4.0 * ((double)x->v.pixels() * C + P * M + (double)M * C * KH * KW);
+  bool use_tc = false;
+  std::shared_ptr<TcWeights> tcw;
+  if (m->opt_conv_path != 1 && tc_supported(a) == 0) {
+    use_tc = true;
+    if (!dry) {
+      std::string key = "tc:" + w->init->name + ":" + std::to_string(Ceff);
+      auto it = m->tc_weights.find(key);
+      if (it == m->tc_weights.end()) {
+        B200_TRY(tc_prepare_weights(dw, M, a.K, m->ctx->stream, &tcw));
+        m->tc_weights[key] = tcw;
+      } else tcw = it->second;
+    }
+  } else if (m->opt_conv_path == 2) {
+    B200_FAIL(B200_EUNSUPPORTED, "Conv %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
+  }
+  if (use_tc) add_step(label, "conv_tc", flops, bytes, [a, tcw](cudaStream_t st) { return launch_conv_tc(a, *tcw, st); });
+  else add_step(label, "conv_simt", flops, bytes, [a](cudaStream_t st) { return launch_conv_simt(a, st); });
+  env[out_name] = y;
+  return 0;
+}
+
+int Planner::do_maxpool(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  Val* x = get(n.input[0]);
+  if (!x || x->rank != 4 || x->is_init) B200_FAIL(B200_EINVAL, "MaxPool %s: input must be a rank-4 activation", n.name.c_str());
+  b200_pool_params p;
+  B200_TRY(parse_pool_attrs(n, &p));
+  int64_t yd[4];
+  B200_TRY(b200_maxpool2d_out_dims(x->dims, &p, yd));
+  Geo g;
+  B200_TRY(ref_geometry(p.auto_pad, (int)x->dims[2], (int)x->dims[3], (int)p.kernel[0], (int)p.kernel[1], (int)p.strides[0], (int)p.strides[1], p.pads, &g));
+  Val y; y.rank = 4; memcpy(y.dims, yd, sizeof(yd));
+  B200_TRY(place(n.output[0], &y));
+  PoolArgs a{};
+  a.x = x->v.p; a.N = x->v.N; a.C = x->v.C; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
+  a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
+  a.kh = (int)p.kernel[0]; a.kw = (int)p.kernel[1]; a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl;
+  const double bytes = 4.0 * ((double)x->v.numel() + (double)y.v.numel());
+  add_step(n.name.empty() ? n.output[0] : n.name, "maxpool", 0, bytes, [a](cudaStream_t st) { return launch_maxpool(a, st); });
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_relu(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  Val* x = get(n.input[0]);
+  if (!x || x->is_init || x->rank != 4) B200_FAIL(B200_EINVAL, "Relu %s: input must be a rank-4 activation (relu_op.rs:16)", n.name.c_str());
+  Val y; y.rank = x->rank; memcpy(y.dims, x->dims, sizeof(y.dims));
+  B200_TRY(place(n.output[0], &y));
+  TView xv = x->v, yv = y.v;
+  add_step(n.name.empty() ? n.output[0] : n.name, "relu", 0, 8.0 * (double)xv.numel(), [xv, yv](cudaStream_t st) { return launch_relu(xv, yv, st); });
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_add(size_t i) {
+  // add(), add_op.rs:16-107: input 2 must be an initializer (:54-68)
+  const WireNode& n = m->wm.nodes[i];
+  if (n.input.size() != 2) B200_FAIL(B200_EINVAL, "Add %s: needs 2 inputs", n.name.c_str());
+  Val* x = get(n.input[0]);
+  const WireTensor* bt = m->wm.find_initializer(n.input[1]);
+  if (!bt) B200_FAIL(B200_EUNSUPPORTED, "Cannot retrieve input 2 for Add operation (add_op.rs:66): %s is not an initializer", n.input[1].c_str());
+  if (!x || x->is_init) B200_FAIL(B200_EUNSUPPORTED, "Add %s: constant first operand is not supported by the graph path", n.name.c_str());
+  auto bd = init_dims(m->wm, *bt);
+  Val y; y.rank = x->rank; memcpy(y.dims, x->dims, sizeof(y.dims));
+  y.perm_C = 0;
+  if (x->rank == 4) {
+    if (bd.size() != 3 || bd[0] != x->dims[1] || bd[1] != 1 || bd[2] != 1)
+      B200_FAIL(B200_EUNSUPPORTED, "Add %s: rank-4 input needs a [C,1,1] initializer (add_op.rs:55-58,75)", n.name.c_str());
+    float* db = nullptr;
+    B200_TRY(vec_const(*bt, (size_t)bd[0], &db));
+    B200_TRY(place(n.output[0], &y));
+    TView xv = x->v, yv = y.v;
+    add_step(n.name.empty() ? n.output[0] : n.name, "add_channel", (double)xv.numel(), 8.0 * (double)xv.numel(),
+             [xv, db, yv](cudaStream_t st) { return launch_add_channel(xv, db, yv, st); });
+  } else if (x->rank == 2) {
+    // reference: same-shape [1,K] + [1,K]; batch-N extension broadcasts the initializer over rows
+    if (bd.size() != 2 || bd[1] != x->dims[1] || (bd[0] != 1 && bd[0] != x->dims[0]))
+      B200_FAIL(B200_EINVAL, "Add %s: rank-2 operands must have the same shape (add_op.rs:84)", n.name.c_str());
+    float* db = nullptr;
+    B200_TRY(vec_const(*bt, (size_t)(bd[0] * bd[1]), &db));
+    B200_TRY(place(n.output[0], &y));
+    TView xv = x->v, yv = y.v, bv;
+    bv.p = db; bv.N = (int)bd[0]; bv.C = (int)bd[1]; bv.H = bv.W = 1; bv.ld = bv.C;
+    add_step(n.name.empty() ? n.output[0] : n.name, "add_rows", (double)xv.numel(), 8.0 * (double)xv.numel(),
+             [xv, bv, yv](cudaStream_t st) { return launch_add_same(xv, bv, yv, st); });
+  } else {
+    B200_FAIL(B200_EUNSUPPORTED, "Add %s: input rank %d", n.name.c_str(), x->rank);
+  }
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_reshape(size_t i) {
+  // reshape(), reshape_op.rs:16-92
+  const WireNode& n = m->wm.nodes[i];
+  if (n.input.size() != 2) B200_FAIL(B200_EINVAL, "Reshape %s: needs 2 inputs", n.name.c_str());
+  const WireTensor* st = m->wm.find_initializer(n.input[1]);
+  if (!st) B200_FAIL(B200_EUNSUPPORTED, "Unable to retrieve Shape for Reshape operation (reshape_op.rs:42)");
+  if (st->i64.size() < 2) B200_FAIL(B200_EINVAL, "Reshape %s: shape must hold >= 2 int64 values (reshape_op.rs:87)", n.name.c_str());
+  Val* x = get(n.input[0]);
+  if (!x || x->rank != 4) B200_FAIL(B200_EINVAL, "Reshape %s: data must be rank 4 (reshape_op.rs:27,30)", n.name.c_str());
+  int64_t s0 = st->i64[0], s1 = st->i64[1];
+  Val y; y.rank = 2;
+  if (x->is_init) {
+    // constant folding: Reshape(initializer) happens once, on the host, in the reference's memory order
+    if (s0 == 0) s0 = x->dims[0];
+    if (s1 == 0) s1 = x->dims[1];
+    const int64_t total = x->dims[0] * x->dims[1] * x->dims[2] * x->dims[3];
+    if (s0 < 0 || s1 < 0 || s0 * s1 != total || (int64_t)x->init->f32.size() != total)
+      B200_FAIL(B200_EINVAL, "Reshape %s: %lldx%lld does not match %lld elements (reshape_op.rs:90)", n.name.c_str(), (long long)s0, (long long)s1, (long long)total);
+    y.dims[0] = s0; y.dims[1] = s1;
+    y.host2d = std::make_shared<std::vector<float>>(x->init->f32);
+    y.is_init = false; y.planned = false;
+    env[n.output[0]] = y;
+    return 0;
+  }
+  // activation: per-image element count is fixed; the leading dim scales with the batch
+  const int64_t static_n = m->in_dims[0] > 0 ? m->in_dims[0] : 1;
+  const int64_t per_image = x->dims[1] * x->dims[2] * x->dims[3];
+  if (s0 == 0) s0 = static_n;
+  if (s1 == 0) s1 = x->dims[1];
+  if (s0 < 0 || s1 <= 0) B200_FAIL(B200_EUNSUPPORTED, "Reshape %s: -1 is not supported (reshape_op.rs:87)", n.name.c_str());
+  if (s0 * s1 != static_n * per_image)
+    B200_FAIL(B200_EINVAL, "Reshape %s: %lldx%lld does not match %lld elements (reshape_op.rs:90)", n.name.c_str(), (long long)s0, (long long)s1, (long long)(static_n * per_image));
+  const int64_t total = x->dims[0] * per_image;
+  y.dims[1] = s1; y.dims[0] = total / s1;
+  const bool order_free = x->v.dense() && (x->v.H * x->v.W == 1 || x->v.C == 1);
+  // Fold the NCHW flatten order into the consumer MatMul's constant weight when possible.
+  bool fold = false;
+  size_t j;
+  if (!order_free && x->v.dense() && s1 == per_image) {
+    if (const WireNode* c = sole_consumer(n.output[0], &j)) {
+      if (c->op_type == "MatMul" && c->input.size() == 2 && c->input[0] == n.output[0]) {
+        Val* b = get(c->input[1]);
+        if (b && b->host2d) fold = true;
+      }
+    }
+  }
+  if (order_free || fold) {
+    y.v.p = x->v.p; y.v.N = (int)y.dims[0]; y.v.C = (int)y.dims[1]; y.v.H = y.v.W = 1; y.v.ld = y.v.C;
+    y.planned = true;
+    if (fold) { y.perm_C = x->v.C; y.perm_HW = x->v.H * x->v.W; }
+  } else {
+    B200_TRY(place(n.output[0], &y));
+    TView xv = x->v; float* dst = y.v.p;
+    add_step(n.name.empty() ? n.output[0] : n.name, "reshape_nchw", 0, 8.0 * (double)xv.numel(),
+             [xv, dst](cudaStream_t st) { return launch_rows_to_nchw(xv, dst, st); });
+  }
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_matmul(size_t i) {
+  // mul(), mul_op.rs:11-32: both operands come from the store's 2-D slot, i.e. from Reshape outputs
+  const WireNode& n = m->wm.nodes[i];
+  if (n.input.size() != 2) B200_FAIL(B200_EINVAL, "MatMul %s: needs 2 inputs", n.name.c_str());
+  Val* a = get(n.input[0]);
+  Val* b = get(n.input[1]);
+  if (!a || !b || a->rank != 2 || b->rank != 2 || a->is_init || b->is_init)
+    B200_FAIL(B200_EINVAL, "MatMul %s: operands must be rank-2 store values (mul_op.rs:16-19 unwrap the 2-D slot)", n.name.c_str());
+  if (!b->host2d) B200_FAIL(B200_EUNSUPPORTED, "MatMul %s: the right operand must be a constant (Reshape of an initializer)", n.name.c_str());
+  if (a->host2d) B200_FAIL(B200_EUNSUPPORTED, "MatMul %s: constant left operand is not supported", n.name.c_str());
+  const int K = (int)a->dims[1], N = (int)b->dims[1];
+  if (b->dims[0] != K) B200_FAIL(B200_EINVAL, "MatMul %s: inner dims %d vs %lld", n.name.c_str(), K, (long long)b->dims[0]);
+  // weight as [N][K] rows (K-contiguous), with the activation's (h,w,c) flatten order folded in if needed
+  std::string key = "matw:" + n.input[1] + ":" + std::to_string(a->perm_C) + "x" + std::to_string(a->perm_HW);
+  float* dw = nullptr;
+  if (!m->consts.count(key)) {
+    std::vector<float> h((size_t)N * K);
+    const std::vector<float>& src = *b->host2d;  // [K][N], k in the reference's (c,h,w) order
+    for (int k = 0; k < K; ++k) {
+      int kp = k;  // position of reference row k in the activation's physical row
+      if (a->perm_C > 0) { const int c = k / a->perm_HW, hw = k % a->perm_HW; kp = hw * a->perm_C + c; }
+      for (int nn = 0; nn < N; ++nn) h[(size_t)nn * K + kp] = src[(size_t)k * N + nn];
+    }
+    B200_TRY(upload_const(m, key, h, &dw));
+  } else dw = m->consts[key]->p;
+  // fuse the following Add of a [1,N] initializer (MNIST Plus214, add_op.rs:84)
+  std::string out_name = n.output[0];
+  std::string label = n.name.empty() ? n.output[0] : n.name;
+  float* dbias = nullptr;
+  size_t j;
+  if (const WireNode* c = sole_consumer(out_name, &j)) {
+    if (c->op_type == "Add" && c->input.size() == 2 && c->input[0] == out_name) {
+      if (const WireTensor* t = m->wm.find_initializer(c->input[1])) {
+        auto d = init_dims(m->wm, *t);
+        if (d.size() == 2 && d[0] == 1 && d[1] == N) {
+          B200_TRY(vec_const(*t, (size_t)N, &dbias));
+          consumed.insert(j); out_name = c->output[0]; label += "+Add";
+        }
+      }
+    }
+  }
+  Val y; y.rank = 2; y.dims[0] = a->dims[0]; y.dims[1] = N;
+  B200_TRY(place(out_name, &y));
+  ConvArgs c{};
+  c.x = a->v.p; c.N = a->v.N; c.C = K; c.H = 1; c.W = 1; c.ldx = a->v.ld;
+  c.w = dw; c.M = N; c.KH = 1; c.KW = 1; c.K = K; c.ldw = K; c.wc = K;
+  c.bias = dbias; c.chan_add = nullptr;
+  c.y = y.v.p; c.Ho = 1; c.Wo = 1; c.ldy = y.v.ld; c.sh = c.sw = 1; c.pt = c.pl = 0; c.relu = 0;
+  const double R = (double)a->dims[0];
+  add_step(label, "matmul_simt", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
+           [c](cudaStream_t st) { return launch_conv_simt(c, st); });
+  env[out_name] = y;
+  return 0;
+}
+
+int Planner::do_concat(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  if (n.input.size() != 2) B200_FAIL(B200_EUNSUPPORTED, "Concat %s: exactly two inputs (concatenate_op.rs:15-18)", n.name.c_str());
+  B200_TRY(attr_check(n, {"axis"}, "CONCATENATE"));
+  const int64_t axis = attr_i(n, "axis", 1);
+  if (axis != 1) B200_FAIL(B200_EUNSUPPORTED, "Concat %s: only axis=1 is implemented", n.name.c_str());
+  Val* a = get(n.input[0]);
+  Val* b = get(n.input[1]);
+  if (!a || !b || a->rank != 4 || b->rank != 4 || a->is_init || b->is_init)
+    B200_FAIL(B200_EINVAL, "Concat %s: inputs must be rank-4 activations (concatenate_op.rs:16,18)", n.name.c_str());
+  if (a->dims[0] != b->dims[0] || a->dims[2] != b->dims[2] || a->dims[3] != b->dims[3])
+    B200_FAIL(B200_EINVAL, "Concat %s: non-axis dims differ", n.name.c_str());
+  auto it = env.find(n.output[0]);
+  if (it != env.end() && it->second.planned && redirect.count(n.input[0])) {
+    return 0;  // both producers already wrote into the result: zero-copy
+  }
+  Val y; y.rank = 4; y.dims[0] = a->dims[0]; y.dims[1] = a->dims[1] + b->dims[1]; y.dims[2] = a->dims[2]; y.dims[3] = a->dims[3];
+  B200_TRY(place(n.output[0], &y));
+  TView av = a->v, bv = b->v, ya = y.v, yb = y.v;
+  ya.C = av.C; yb.C = bv.C; if (!dry) yb.p += av.C;
+  std::string nm = n.name.empty() ? n.output[0] : n.name;
+  add_step(nm + ":0", "concat_copy", 0, 8.0 * (double)av.numel(), [av, ya](cudaStream_t st) { return launch_copy_rows(av, ya, st); });
+  add_step(nm + ":1", "concat_copy", 0, 8.0 * (double)bv.numel(), [bv, yb](cudaStream_t st) { return launch_copy_rows(bv, yb, st); });
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_dropout(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  B200_TRY(attr_check(n, {"ratio"}, "DROP OUT"));  // dropout_op.rs:22-28
+  Val* x = get(n.input[0]);
+  if (!x || x->rank != 4 || x->is_init) B200_FAIL(B200_EINVAL, "Dropout %s: input must be a rank-4 activation", n.name.c_str());
+  env[n.output[0]] = *x;  // identity at inference (dropout_op.rs:66-71): alias, no kernel
+  return 0;
+}
+
+int Planner::do_gap(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  Val* x = get(n.input[0]);
+  if (!x || x->rank != 4 || x->is_init) B200_FAIL(B200_EINVAL, "GlobalAveragePool %s: input must be a rank-4 activation", n.name.c_str());
+  size_t j;
+  const WireNode* c = sole_consumer(n.output[0], &j);
+  TView xv = x->v;
+  if (c && c->op_type == "Softmax" && (size_t)xv.C * sizeof(float) <= 48 * 1024) {
+    // SqueezeNet tail: GAP + Softmax in one kernel (global_average_pool_op.rs:33-52 + softmax_op.rs:45-57)
+    consumed.insert(j);
+    Val y; y.rank = 2; y.dims[0] = x->dims[0]; y.dims[1] = x->dims[1];
+    B200_TRY(place(c->output[0], &y));
+    float* dst = y.v.p;
+    add_step((n.name.empty() ? n.output[0] : n.name) + "+Softmax", "gap_softmax", (double)xv.numel(), 4.0 * ((double)xv.numel() + (double)y.v.numel()),
+             [xv, dst](cudaStream_t st) { return launch_gap_softmax(xv, dst, st); });
+    env[c->output[0]] = y;
+    return 0;
+  }
+  Val y; y.rank = 4; y.dims[0] = x->dims[0]; y.dims[1] = x->dims[1]; y.dims[2] = 1; y.dims[3] = 1;
+  B200_TRY(place(n.output[0], &y));
+  TView yv = y.v;
+  add_step(n.name.empty() ? n.output[0] : n.name, "global_avgpool", (double)xv.numel(), 4.0 * ((double)xv.numel() + (double)yv.numel()),
+           [xv, yv](cudaStream_t st) { return launch_global_avgpool(xv, yv, st); });
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::do_softmax(size_t i) {
+  const WireNode& n = m->wm.nodes[i];
+  Val* x = get(n.input[0]);
+  if (!x || x->rank != 4 || x->is_init) B200_FAIL(B200_EINVAL, "Softmax %s: input must be a rank-4 activation (softmax_op.rs:18)", n.name.c_str());
+  Val y; y.rank = 2; y.dims[0] = x->dims[0]; y.dims[1] = x->dims[1] * x->dims[2] * x->dims[3];
+  B200_TRY(place(n.output[0], &y));
+  TView xv = x->v; float* dst = y.v.p;
+  add_step(n.name.empty() ? n.output[0] : n.name, "softmax", 4.0 * (double)xv.numel(), 8.0 * (double)xv.numel(),
+           [xv, dst](cudaStream_t st) { return launch_softmax(xv, dst, st); });
+  env[n.output[0]] = y;
+  return 0;
+}
+
+int Planner::run() {
+  env.clear(); consumed.clear(); arena_cursor = 0; arena_allocs.clear();
+  n_consumers.clear();
+  for (auto& n : m->wm.nodes) for (auto& in : n.input) n_consumers[in]++;
+  redirect.clear();
+  B200_TRY(plan_concat_redirects());
+  // graph input
+  Val in; in.rank = 4; in.dims[0] = B * (m->in_dims[0] > 0 ? m->in_dims[0] : 1);
+  in.dims[1] = m->in_dims[1]; in.dims[2] = m->in_dims[2]; in.dims[3] = m->in_dims[3];
+  in.v.N = (int)in.dims[0]; in.v.C = (int)in.dims[1]; in.v.H = (int)in.dims[2]; in.v.W = (int)in.dims[3];
+  in.v.ld = in.v.C >= 3 ? round_up4(in.v.C) : in.v.C;
+  in.v.p = arena_alloc((size_t)in.v.pixels() * in.v.ld);
+  in.planned = true; in.pad_zeroed = true;
+  env[m->input_name] = in;
+  plan->in_view = in.v;
+  plan->in_zero_pad = in.v.ld != in.v.C;
+  plan->in_direct = in.v.dense() && (in.v.C == 1 || in.v.H * in.v.W == 1);
+
+  // Concat results need their dims before the producers run: shape-only evaluation happens naturally in
+  // file order because each producer's `place` looks the parent up in env; so register Concat outputs
+  // lazily: when the first redirected producer is placed, the parent's dims must exist.  Compute them here
+  // with a light shape walk (Conv / MaxPool / Relu / Dropout / Concat are the only rank-4 -> rank-4 ops).
+  {
+    std::map<std::string, std::vector<int64_t>> shp;
+    shp[m->input_name] = {in.dims[0], in.dims[1], in.dims[2], in.dims[3]};
+    for (auto& n : m->wm.nodes) {
+      auto have = [&](const std::string& s) { return shp.count(s) > 0; };
+      if (n.input.empty() || n.output.empty()) continue;
+      if (n.op_type == "Conv" && have(n.input[0])) {
+        const WireTensor* w = n.input.size() > 1 ? m->wm.find_initializer(n.input[1]) : nullptr;
+        if (!w) continue;
+        auto wd = init_dims(m->wm, *w);
+        if (wd.size() != 4) continue;
+        b200_conv_params p;
+        if (parse_conv_attrs(n, &p)) continue;
+        int64_t xd[4], wdd[4], yd[4];
+        for (int k = 0; k < 4; ++k) { xd[k] = shp[n.input[0]][k]; wdd[k] = wd[k]; }
+        if (b200_conv2d_out_dims(xd, wdd, &p, yd)) continue;
+        shp[n.output[0]] = {yd[0], yd[1], yd[2], yd[3]};
+      } else if (n.op_type == "MaxPool" && have(n.input[0])) {
+        b200_pool_params p;
+        if (parse_pool_attrs(n, &p)) continue;
+        int64_t xd[4], yd[4];
+        for (int k = 0; k < 4; ++k) xd[k] = shp[n.input[0]][k];
+        if (b200_maxpool2d_out_dims(xd, &p, yd)) continue;
+        shp[n.output[0]] = {yd[0], yd[1], yd[2], yd[3]};
+      } else if ((n.op_type == "Relu" || n.op_type == "Dropout" || n.op_type == "Add") && have(n.input[0])) {
+        shp[n.output[0]] = shp[n.input[0]];
+      } else if (n.op_type == "Concat" && n.input.size() == 2 && have(n.input[0]) && have(n.input[1])) {
+        auto a = shp[n.input[0]], b = shp[n.input[1]];
+        shp[n.output[0]] = {a[0], a[1] + b[1], a[2], a[3]};
+      }
+    }
+    // fix channel offsets; drop redirects whose shapes are unknown or whose offsets break 16-byte alignment
+    std::vector<std::string> drop;
+    for (auto& n : m->wm.nodes) {
+      if (n.op_type != "Concat" || n.input.size() != 2) continue;
+      if (!redirect.count(n.input[0]) || redirect[n.input[0]].first != n.output[0]) continue;
+      bool ok = shp.count(n.input[0]) && shp.count(n.input[1]) && shp.count(n.output[0]);
+      if (ok) {
+        auto a = shp[n.input[0]], b = shp[n.input[1]];
+        ok = a[0] == b[0] && a[2] == b[2] && a[3] == b[3];
+        if (ok) {
+          redirect[n.input[1]].second = (int)a[1];
+          Val parent; parent.rank = 4;
+          for (int k = 0; k < 4; ++k) parent.dims[k] = shp[n.output[0]][k];
+          env[n.output[0]] = parent;
+        }
+      }
+      if (!ok) { drop.push_back(n.input[0]); drop.push_back(n.input[1]); }
+    }
+    for (auto& d : drop) redirect.erase(d);
+  }
+
+  for (size_t i = 0; i < m->wm.nodes.size(); ++i) {
+    if (consumed.count(i)) continue;
+    const WireNode& n = m->wm.nodes[i];
+    if (n.input.empty() || n.output.empty()) B200_FAIL(B200_EINVAL, "node %zu (%s) has no inputs/outputs", i, n.op_type.c_str());
+    const std::string& op = n.op_type;
+    if (op == "Conv") B200_TRY(do_conv(i));
+    else if (op == "Relu") B200_TRY(do_relu(i));
+    else if (op == "MaxPool") B200_TRY(do_maxpool(i));
+    else if (op == "Concat") B200_TRY(do_concat(i));
+    else if (op == "Dropout") B200_TRY(do_dropout(i));
+    else if (op == "GlobalAveragePool") B200_TRY(do_gap(i));
+    else if (op == "Softmax") B200_TRY(do_softmax(i));
+    else if (op == "Reshape") B200_TRY(do_reshape(i));
+    else if (op == "Add") B200_TRY(do_add(i));
+    else if (op == "MatMul") B200_TRY(do_matmul(i));
+    else B200_FAIL(B200_EUNSUPPORTED, "INFERENCE OPERATION '%s' NOT FOUND FOR NODE %s", op.c_str(), n.name.c_str());  // model_inference.rs:158
+  }
+  // ---- result: the value the reference prints (Softmax result / final Add) == graph.output[0] for both models
+  std::string out_name = m->wm.outputs.empty() ? m->wm.nodes.back().output[0] : m->wm.outputs[0].name;
+  auto it = env.find(out_name);
+  if (it == env.end() || !it->second.planned) {
+    // fall back to the last produced activation (e.g. the output was folded into a fused step)
+    for (auto r = m->wm.nodes.rbegin(); r != m->wm.nodes.rend() && (it == env.end() || !it->second.planned); ++r)
+      it = env.find(r->output[0]);
+    if (it == env.end() || !it->second.planned) B200_FAIL(B200_EINVAL, "graph output %s was not produced", out_name.c_str());
+  }
+  Val& o = it->second;
+  plan->out_per_image = o.v.numel() / std::max<int64_t>(1, B);
+  plan->out_view = o.v;
+  if (o.rank == 4 && o.v.H * o.v.W > 1 && o.v.C > 1) {
+    plan->out_needs_nchw = true;
+    plan->out_ptr = arena_alloc((size_t)o.v.numel());
+  } else if (!o.v.dense()) {
+    plan->out_needs_nchw = true;  // strided rows -> dense copy via the same kernel (HW == 1 or C == 1)
+    plan->out_ptr = arena_alloc((size_t)o.v.numel());
+  } else {
+    plan->out_needs_nchw = false;
+    plan->out_ptr = o.v.p;
+  }
+  if (plan->out_needs_nchw && !dry) {
+    TView ov = o.v; float* dst = plan->out_ptr;
+    add_step("output_to_nchw", "reshape_nchw", 0, 8.0 * (double)ov.numel(), [ov, dst](cudaStream_t st) { return launch_rows_to_nchw(ov, dst, st); });
+  }
+  return 0;
+}
+
+int build_plan(b200_model* m, int64_t batch, Plan** out) {
+  auto it = m->plans.find(batch);
+  if (it != m->plans.end()) { *out = it->second.get(); return 0; }
+  if (batch <= 0) B200_FAIL(B200_EINVAL, "batch must be positive");
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->batch = batch;
+  Planner pl;
+  pl.m = m; pl.plan = plan.get(); pl.B = batch;
+  pl.dry = true;
+  B200_TRY(pl.run());
+  plan->arena.reset(new DevBuf());
+  plan->arena->bytes = pl.arena_cursor + 256;
+  if (cudaMalloc((void**)&plan->arena->p, plan->arena->bytes) != cudaSuccess) {
+    cudaGetLastError();
+    B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for the activation arena (batch %lld)", plan->arena->bytes, (long long)batch);
+  }
+  plan->arena_used = pl.arena_cursor;
+  pl.dry = false;
+  B200_TRY(pl.run());
+  B200_CUDA(cudaStreamSynchronize(m->ctx->stream));  // constant uploads / weight preparation done
+  *out = plan.get();
+  m->plans[batch] = std::move(plan);
+  return 0;
+}
+
+int run_steps(b200_model* m, Plan* plan, cudaStream_t st) {
+  for (auto& s : plan->steps) {
+    int rc = s.run(st);
+    if (rc) return rc;
+  }
+  (void)m;
+  return 0;
+}
+
+int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out) {
+  cudaStream_t st = m->ctx->stream;
+  // 1. input: logical NCHW (what the reference's manage_input_data holds, utils.rs:29-45) -> channels-last rows
+  if (plan->in_direct) {
+    B200_CUDA(cudaMemcpyAsync(plan->in_view.p, d_in, (size_t)plan->in_view.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    B200_TRY(launch_nchw_to_rows(d_in, plan->in_view, plan->in_zero_pad, st));
+    m->ctx->launches++;
+  }
+  // 2. the node walk, replayed as one CUDA graph
+  if (m->opt_cuda_graph) {
+    if (!plan->graph_exec) {
+      cudaGraph_t g = nullptr;
+      B200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = run_steps(m, plan, st);
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) B200_FAIL(B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      e = cudaGraphInstantiate(&plan->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) B200_FAIL(B200_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    B200_CUDA(cudaGraphLaunch(plan->graph_exec, st));
+  } else {
+    B200_TRY(run_steps(m, plan, st));
+  }
+  m->ctx->launches += (int64_t)plan->steps.size();
+  // 3. result
+  if (d_out != plan->out_ptr)
+    B200_CUDA(cudaMemcpyAsync(d_out, plan->out_ptr, (size_t)plan->batch * plan->out_per_image * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" {
+
+int b200_model_load_onnx(b200_ctx* ctx, const uint8_t* bytes, size_t len, b200_model** out) {
+  if (!ctx || !bytes || !out) B200_FAIL(B200_EINVAL, "NULL argument");
+  std::unique_ptr<b200_model> m(new b200_model());
+  m->ctx = ctx;
+  std::string err;
+  if (!parse_model(bytes, len, &m->wm, &err)) B200_FAIL(B200_EPARSE, "ONNX parse error: %s", err.c_str());
+  if (m->wm.nodes.empty()) B200_FAIL(B200_EPARSE, "ONNX graph has no nodes");
+  // the single data input: the graph.input entries that are not initializers (utils.rs:35)
+  int found = 0;
+  for (auto& vi : m->wm.inputs) {
+    if (m->wm.find_initializer(vi.name)) continue;
+    ++found;
+    m->input_name = vi.name;
+    if (vi.dims.size() != 4) B200_FAIL(B200_EUNSUPPORTED, "input %s: the reference needs 4 static dims (utils.rs:36-40)", vi.name.c_str());
+    for (int i = 0; i < 4; ++i) {
+      if (vi.dims[i] <= 0 && i > 0) B200_FAIL(B200_EUNSUPPORTED, "input %s: symbolic dim (utils.rs:67 panics on DimParam)", vi.name.c_str());
+      m->in_dims[i] = vi.dims[i] > 0 ? vi.dims[i] : 1;
+    }
+  }
+  if (found != 1) B200_FAIL(B200_EUNSUPPORTED, "expected exactly one non-initializer graph input, found %d", found);
+  Guard g(ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m.get(), 1, &p));  // validates every node up front (unknown op / attribute errors surface here)
+  m->out_per_image = p->out_per_image;
+  *out = m.release();
+  return 0;
+}
+
+int b200_model_load_file(b200_ctx* ctx, const char* path, b200_model** out) {
+  if (!path) B200_FAIL(B200_EINVAL, "path is NULL");
+  std::ifstream f(path, std::ios::binary);
+  if (!f) B200_FAIL(B200_EINVAL, "cannot open %s", path);
+  std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  return b200_model_load_onnx(ctx, (const uint8_t*)buf.data(), buf.size(), out);
+}
+
+int b200_model_free(b200_model* m) {
+  if (!m) return 0;
+  Guard g(m->ctx);
+  cudaStreamSynchronize(m->ctx->stream);
+  delete m;
+  return 0;
+}
+
+int b200_model_io(const b200_model* m, int64_t in_chw[3], int64_t* out_per_image) {
+  if (!m) B200_FAIL(B200_EINVAL, "model is NULL");
+  if (in_chw) { in_chw[0] = m->in_dims[1]; in_chw[1] = m->in_dims[2]; in_chw[2] = m->in_dims[3]; }
+  if (out_per_image) *out_per_image = m->out_per_image;
+  return 0;
+}
+
+int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
+  if (!m || !key) B200_FAIL(B200_EINVAL, "NULL argument");
+  Guard g(m->ctx);
+  std::string k(key);
+  if (k == "cuda_graph") m->opt_cuda_graph = value ? 1 : 0;
+  else if (k == "conv_path") {
+    if (value < 0 || value > 2) B200_FAIL(B200_EINVAL, "conv_path must be 0, 1 or 2");
+    if (m->opt_conv_path != (int)value) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_conv_path = (int)value;
+  } else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
+  else B200_FAIL(B200_EINVAL, "unknown option %s", key);
+  return 0;
+}
+
+int b200_model_run_device(b200_model* m, const float* d_in, int64_t batch, float* d_out) {
+  if (!m || !d_in || !d_out) B200_FAIL(B200_EINVAL, "NULL argument");
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m, batch, &p));
+  return run_plan(m, p, d_in, d_out);
+}
+
+int b200_model_run(b200_model* m, const float* host_in, int64_t batch, float* host_out) {
+  if (!m || !host_in || !host_out) B200_FAIL(B200_EINVAL, "NULL argument");
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m, batch, &p));
+  const size_t in_bytes = (size_t)batch * m->in_dims[0] * m->in_dims[1] * m->in_dims[2] * m->in_dims[3] * sizeof(float);
+  const size_t out_bytes = (size_t)batch * p->out_per_image * sizeof(float);
+  if (m->stage_in_bytes < in_bytes) {
+    if (m->stage_in) cudaFree(m->stage_in);
+    m->stage_in = nullptr; m->stage_in_bytes = 0;
+    if (cudaMalloc((void**)&m->stage_in, in_bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for input staging", in_bytes); }
+    m->stage_in_bytes = in_bytes;
+  }
+  if (m->stage_out_bytes < out_bytes) {
+    if (m->stage_out) cudaFree(m->stage_out);
+    m->stage_out = nullptr; m->stage_out_bytes = 0;
+    if (cudaMalloc((void**)&m->stage_out, out_bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for output staging", out_bytes); }
+    m->stage_out_bytes = out_bytes;
+  }
+  cudaStream_t st = m->ctx->stream;
+  B200_CUDA(cudaMemcpyAsync(m->stage_in, host_in, in_bytes, cudaMemcpyHostToDevice, st));
+  B200_TRY(run_plan(m, p, m->stage_in, m->stage_out));
+  B200_CUDA(cudaMemcpyAsync(host_out, m->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int64_t b200_model_launches_per_run(b200_model* m, int64_t batch) {
+  if (!m) return B200_EINVAL;
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  if (build_plan(m, batch, &p)) return B200_EINVAL;
+  return (int64_t)p->steps.size() + (p->in_direct ? 0 : 1);
+}
+
+int b200_model_profile(b200_model* m, int64_t batch, int iters, int flush_l2, char* buf, size_t cap) {
+  if (!m || !buf || cap < 64) B200_FAIL(B200_EINVAL, "bad arguments");
+  if (iters < 1) iters = 1;
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m, batch, &p));
+  cudaStream_t st = m->ctx->stream;
+  const size_t flush_bytes = 256u << 20;
+  if (flush_l2 && !m->ctx->l2_flush) {
+    if (cudaMalloc((void**)&m->ctx->l2_flush, flush_bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc for the L2 flush buffer"); }
+  }
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  std::ostringstream js;
+  js << "[";
+  // the input transform is part of every run: profile it as step 0 (reads its own output buffer as source shape only)
+  int rc = 0;
+  for (size_t i = 0; i < p->steps.size() && rc == 0; ++i) {
+    Step& s = p->steps[i];
+    double total_ms = 0;
+    rc = s.run(st);  // warm
+    for (int it = 0; it < iters && rc == 0; ++it) {
+      if (flush_l2) launch_fill_zero(m->ctx->l2_flush, flush_bytes / sizeof(float), st);
+      cudaEventRecord(e0, st);
+      rc = s.run(st);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { rc = B200_ECUDA; set_error("profile: step %s failed: %s", s.name.c_str(), cudaGetErrorString(cudaGetLastError())); break; }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      total_ms += ms;
+    }
+    if (i) js << ",";
+    js << "{\"name\":\"" << s.name << "\",\"kind\":\"" << s.kind << "\",\"ms\":" << (total_ms / iters) << ",\"flops\":" << s.flops
+       << ",\"bytes\":" << s.bytes << "}";
+  }
+  js << "]";
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) return rc;
+  std::string out = js.str();
+  if (out.size() + 1 > cap) B200_FAIL(B200_EINVAL, "profile buffer too small: need %zu bytes", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+int b200_tensorproto_read(const uint8_t* bytes, size_t len, float* out, size_t cap, int64_t* dims_out, int* rank_out, size_t* n) {
+  if (!bytes || !n) B200_FAIL(B200_EINVAL, "NULL argument");
+  WireTensor t;
+  std::string err;
+  if (!parse_tensor(bytes, len, &t, &err)) B200_FAIL(B200_EPARSE, "%s", err.c_str());
+  if (t.f32.empty() && !t.i64.empty()) B200_FAIL(B200_EUNSUPPORTED, "TensorProto holds int64 data; read_input_data (main.rs:44-53) reads f32");
+  *n = t.f32.size();
+  if (rank_out) *rank_out = (int)t.dims.size();
+  if (dims_out) for (size_t i = 0; i < t.dims.size() && i < 8; ++i) dims_out[i] = t.dims[i];
+  if (out) memcpy(out, t.f32.data(), std::min(cap, t.f32.size()) * sizeof(float));
+  return 0;
+}
+
+}  // extern "C"

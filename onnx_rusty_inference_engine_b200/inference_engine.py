@@ -1,0 +1,127 @@
+"""The reference's executor surface (src/inference_engine/model_inference.rs) over the B200 backend.
+
+Two ways to run a model, both entirely on the device:
+
+  * `inference(model, input_data, input_tensor_name)` -- the reference's node-by-node walk
+    (model_inference.rs:29-120, dispatch :128-162): one C-ABI operator call per node, activations stay in HBM
+    in a `Store`.  Kept for drop-in parity with the per-op interface and used by the op-level tests.
+  * `Engine` -- the graph-level path (b200_model_*): weights uploaded once, Conv+Add+Relu / Concat / Dropout /
+    Reshape fused or elided, the node sequence replayed as one CUDA graph.  This is what bench.py times.
+
+The reference returns () and prints; both paths here also return the result array.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from . import inference_fp32_ops as ops
+from . import onnx_proto as P
+from ._lib import B200Error
+
+_default_ctx: Optional[L.Context] = None
+
+
+def default_context() -> L.Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = L.Context(0)
+    return _default_ctx
+
+
+def manage_input_data(store: ops.Store, model, input_data: np.ndarray, input_tensor_name: Sequence[str]) -> None:
+    """manage_input_data, utils.rs:29-45: names that are initializers are skipped (:35); every other name
+    receives the same input_data shaped by graph.input's static dims (:36-40)."""
+    g = model.graph
+    for name in input_tensor_name:
+        if ops.already_into_initializer(g.initializer, name):
+            continue
+        vi = next((v for v in g.input if v.name == name), None)
+        if vi is None:
+            raise B200Error(-1, f"input {name} not found in graph.input (utils.rs:36)")
+        dims = P.value_info_dims(vi)
+        if len(dims) != 4 or any(d < 0 for d in dims):
+            raise B200Error(-2, f"input {name}: need 4 static dims (utils.rs:36-40, :67)")
+        flat = np.asarray(input_data, dtype=np.float32).reshape(-1)
+        if flat.size != int(np.prod(dims)):
+            raise B200Error(-1, "input length != static model shape (utils.rs:40 from_shape_vec unwrap)")
+        store[name] = (None, store.ctx.tensor(flat.reshape(dims)))
+
+
+def node_inference(node, store: ops.Store, model, verbose: bool = False) -> None:
+    """node_inference, model_inference.rs:128-162."""
+    if verbose:
+        print(f"INFERENCE ON INPUT(s) {list(node.input)} ON {node.op_type} OPERATION done by MAIN PROCESS")
+    g = model.graph
+    op = node.op_type
+    if op == "Conv":
+        ops.convolution(store, node, g.input, g.initializer)
+    elif op == "Relu":
+        ops.relu(store, node)
+    elif op == "MaxPool":
+        ops.max_pool(store, node, g.input, g.initializer)
+    elif op == "Concat":
+        ops.concatenation(store, node)
+    elif op == "Dropout":
+        ops.drop_out(store, node)
+    elif op == "GlobalAveragePool":
+        ops.global_average_pool(store, node)
+    elif op == "Softmax":
+        ops.softmax(store, node)
+    elif op == "Reshape":
+        ops.reshape(store, node, g.input, g.initializer)
+    elif op == "Add":
+        ops.add(store, node, g.input, g.initializer)
+    elif op == "MatMul":
+        ops.mul(store, node)
+    else:
+        raise B200Error(-2, f"INFERENCE OPERATION '{op}' NOT FOUND FOR NODE {node.name}")  # model_inference.rs:158
+
+
+def inference(model, input_data, input_tensor_name: Sequence[str], ctx: Optional[L.Context] = None,
+              verbose: bool = False) -> np.ndarray:
+    """inference(), model_inference.rs:29.  `model` is a decoded ModelProto (onnx_proto.load_model).
+    Nodes run in file order on one stream; the reference's branch threads (multithreading/*.rs) only change
+    which host thread issues a node, never the result."""
+    ctx = ctx or default_context()
+    store = ops.Store(ctx)
+    manage_input_data(store, model, input_data, input_tensor_name)
+    for node in model.graph.node:
+        node_inference(node, store, model, verbose)
+    res = store.last_result
+    if res is None:
+        name = model.graph.output[0].name if model.graph.output else model.graph.node[-1].output[0]
+        s2, s4 = store[name]
+        res = s2 if s2 is not None else s4
+    out = res.numpy()
+    return out.reshape(out.shape[0], -1)
+
+
+class Engine:
+    """Graph-level executor for one GPU (wraps b200_model)."""
+
+    def __init__(self, onnx_file, device: int = 0, stream: Optional[int] = None, ctx: Optional[L.Context] = None):
+        self.ctx = ctx or L.Context(device, stream)
+        self.model = L.Model(self.ctx, onnx_file)
+        self.in_chw = self.model.in_chw
+        self.out_per_image = self.model.out_per_image
+
+    def __call__(self, x: np.ndarray) -> np.ndarray:
+        return self.model.run(x)
+
+    def run_torch(self, x, out=None):
+        """x: contiguous float32 CUDA tensor [N,C,H,W] on this engine's device; returns [N, out_per_image].
+        Asynchronous on the engine's stream (pass torch's current stream at construction to stay ordered)."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, self.out_per_image), dtype=torch.float32, device=x.device)
+        self.model.run_raw(x.data_ptr(), n, out.data_ptr(), device=True)
+        return out
+
+    def run_pinned(self, x_host, out_host) -> None:
+        """Host-to-host through the C ABI with caller-provided (ideally pinned) torch CPU tensors."""
+        self.model.run_raw(x_host.data_ptr(), x_host.shape[0], out_host.data_ptr(), device=False)

@@ -1,0 +1,141 @@
+"""End-to-end parity on the GPU (BASELINE.json configs 1, 3, 4, 5 at test sizes):
+MNIST-8 against the reference's bundled golden pair, batch-N against N independent batch-1 oracle runs, synthetic
+SqueezeNet1.0 against the oracle, and size-independent properties at the full batch sizes (batch-position
+invariance: image i of a batch-256 run is bitwise the batch-1 result; softmax rows sum to 1)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, MNIST_ONNX, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden():
+    from oracle import onnx_wire as ow
+    x = ow.load_tensor_pb(os.path.join(GOLDEN, "mnist_data_0.pb")).astype(np.float32)
+    y = ow.load_tensor_pb(os.path.join(GOLDEN, "mnist_output_0.pb")).reshape(1, -1)
+    return x, y
+
+
+def test_mnist_golden_engine(ctx):
+    """Config 1 through the graph-level path (b200_model_run)."""
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    x, want = _golden()
+    eng = Engine(MNIST_ONNX, ctx=ctx)
+    assert eng.in_chw == (1, 28, 28) and eng.out_per_image == 10
+    got = eng(x.reshape(1, 1, 28, 28))
+    assert_close(got, want, "mnist golden (engine)")
+    assert int(got.argmax()) == int(want.argmax()) == 2
+    eng.model.set_option("cuda_graph", 0)
+    assert np.array_equal(eng(x.reshape(1, 1, 28, 28)), got), "graph replay and direct launches must agree bitwise"
+
+
+def test_mnist_golden_node_walk(ctx):
+    """Config 1 through the reference-shaped per-node interface: inference() -> node_inference() -> op functions."""
+    from onnx_rusty_inference_engine_b200 import onnx_proto as P
+    from onnx_rusty_inference_engine_b200.inference_engine import inference
+    x, want = _golden()
+    model = P.load_model(MNIST_ONNX)
+    got = inference(model, x, ["Input3", "Parameter193"], ctx=ctx)   # names as in main.rs:14
+    assert_close(got, want, "mnist golden (node walk)")
+    assert int(got.argmax()) == 2
+
+
+def test_group17_entry_point(capsys):
+    from onnx_rusty_inference_engine_b200 import group17
+    x, want = _golden()
+    got = group17.onnx_make_inference(MNIST_ONNX, os.path.join(GOLDEN, "mnist_data_0.pb"),
+                                      os.path.join(GOLDEN, "mnist_output_0.pb"), ["Input3", "Parameter193"])
+    assert_close(got, want, "group17")
+    out = capsys.readouterr().out
+    assert "MNist-8 Inference results: Class 3-nth predicted." in out   # 1-based class, add_op.rs:100-104
+    assert "Expected Data:" in out                                       # main.rs:41
+
+
+def test_mnist_batch_vs_oracle(ctx):
+    """Config 5 at test size: batch 64 of N(0,10^2) images == 64 batch-1 oracle runs; batch-position invariant."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(64, chw=(1, 28, 28), seed=3)
+    want = rm.run_batch(ow.load_model(MNIST_ONNX), xs, ["Input3", "Parameter193"], threads=4)
+    eng = Engine(MNIST_ONNX, ctx=ctx)
+    got = eng(xs)
+    assert_close(got, want, "mnist batch 64")
+    assert (got.argmax(1) == want.argmax(1)).all()
+    one = eng(xs[17:18])
+    assert np.array_equal(one[0], got[17]), "batch-position invariance (bitwise)"
+    big = eng(np.tile(xs, (64, 1, 1, 1)))          # 4096 images: same 64 answers, 64 times
+    assert np.array_equal(big.reshape(64, 64, 10), np.broadcast_to(got, (64, 64, 10)))
+
+
+def test_squeezenet_synth_vs_oracle(ctx, synth_onnx):
+    """Config 3 at test size: 6 seeded images through all 66 nodes vs the oracle, both executors."""
+    from onnx_rusty_inference_engine_b200 import onnx_proto as P, synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine, inference
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(6, seed=1)
+    want = rm.run_batch(ow.load_model(synth_onnx), xs, threads=6)
+    eng = Engine(synth_onnx, ctx=ctx)
+    got = eng(xs)
+    assert got.shape == (6, 1000)
+    assert_close(got, want, "squeezenet synth (engine)")
+    assert (got.argmax(1) == want.argmax(1)).all()
+    walk = inference(P.load_model(synth_onnx), xs[0], ["data_0"], ctx=ctx)
+    assert_close(walk, want[0:1], "squeezenet synth (node walk)")
+    eng.model.set_option("conv_path", 1)   # CUDA-core cross-check path must agree with the default path
+    got_simt = eng(xs)
+    assert_close(got_simt, want, "squeezenet synth (conv_path=1)")
+
+
+def test_squeezenet_batch_properties(ctx, synth_onnx):
+    """Config 3 at full size (batch 256): batch-position invariance and softmax normalisation."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    eng = Engine(synth_onnx, ctx=ctx)
+    xs = synth.synthetic_batch(8, seed=2)
+    ref8 = eng(xs)
+    big = eng(np.tile(xs, (32, 1, 1, 1)))          # 256 images
+    assert big.shape == (256, 1000)
+    assert np.array_equal(big.reshape(32, 8, 1000), np.broadcast_to(ref8, (32, 8, 1000))), "batch-position invariance"
+    assert np.allclose(big.sum(1), 1.0, atol=1e-5)
+    assert np.isfinite(big).all() and (big >= 0).all()
+
+
+def test_engine_on_torch_stream(synth_onnx):
+    """Device-resident entry (b200_model_run_device) on torch's current stream, input/outputs as torch tensors."""
+    import torch
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    torch.cuda.set_device(0)
+    s = torch.cuda.Stream()
+    xs = synth.synthetic_batch(4, seed=5)
+    with torch.cuda.stream(s):
+        eng = Engine(synth_onnx, device=0, stream=s.cuda_stream)
+        host = eng(xs)
+        dev = eng.run_torch(torch.from_numpy(xs).cuda())
+        s.synchronize()   # only this stream: the backend's work must have been ordered on it
+        assert np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_unknown_op_and_attr_are_errors(ctx):
+    """model_inference.rs:158 (unknown op) and convolution_op.rs:160 (unknown attribute) panic upstream; here they
+    are B200_EUNSUPPORTED at load time."""
+    from onnx_rusty_inference_engine_b200 import _lib as L, onnx_proto as P
+    w = np.zeros((2, 1, 1, 1), np.float32)
+    def model(nodes):
+        g = {"node": nodes, "name": "t", "initializer": [P.make_tensor("w", w)],
+             "input": [P.make_value_info("x", [1, 1, 4, 4]), P.make_value_info("w", w.shape)],
+             "output": [P.make_value_info("y", [1, 2, 4, 4])]}
+        return P.encode("ModelProto", {"ir_version": 3, "graph": g, "opset_import": [{"domain": "", "version": 8}]})
+    with pytest.raises(L.B200Error, match="NOT FOUND FOR NODE"):
+        L.Model(ctx, model([P.make_node("Sigmoid", ["x"], ["y"], name="s")]))
+    with pytest.raises(L.B200Error, match="ATTRIBUTE NAME FOR CONVOLUTION NOT FOUND"):
+        L.Model(ctx, model([P.make_node("Conv", ["x", "w"], ["y"], name="c", strides=[1, 1], foo=1)]))
+    with pytest.raises(L.B200Error, match="strides"):
+        L.Model(ctx, model([P.make_node("Conv", ["x", "w"], ["y"], name="c")]))
+    ok = L.Model(ctx, model([P.make_node("Conv", ["x", "w"], ["y"], name="c", strides=[1, 1])]))
+    out = ok.run(np.ones((3, 1, 4, 4), np.float32))
+    assert out.shape == (3, 32) and np.array_equal(out, np.zeros((3, 32), np.float32))
