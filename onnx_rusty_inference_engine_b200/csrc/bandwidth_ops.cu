@@ -148,7 +148,7 @@ __device__ float block_max(float v, float* red) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+  float r = ((threadIdx.x & 31) < (blockDim.x >> 5)) ? red[threadIdx.x & 31] : -INFINITY;
   r = warp_max(r);
   __syncthreads();
   return r;
@@ -157,7 +157,7 @@ __device__ float block_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  float r = ((threadIdx.x & 31) < (blockDim.x >> 5)) ? red[threadIdx.x & 31] : 0.f;
   r = warp_sum(r);
   __syncthreads();
   return r;

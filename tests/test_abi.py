@@ -1,0 +1,98 @@
+"""The C-ABI library without a GPU: it loads, exports every symbol include/b200rt.h declares, refuses to run
+without a device (no CPU fallback) and its host-side geometry matches the oracle's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from onnx_rusty_inference_engine_b200 import _lib as L
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "b200rt.h")) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = _declared_symbols()
+    assert len(syms) >= 35
+    lib = C.CDLL(L.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200rt.h but not exported"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature in _lib.py"
+    assert set(L.SIGNATURES) == set(syms)
+    assert L.lib().b200_version().startswith(b"b200rt")
+
+
+def test_no_cpu_fallback():
+    if L.lib().b200_device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(L.B200Error) as e:
+        L.Context(0)
+    assert e.value.code == -6   # B200_ENODEVICE
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    with pytest.raises(L.B200Error):
+        Engine(os.path.join(ROOT, "tests", "golden", "mnist-8.onnx"))
+
+
+def _conv_dims(x, w, strides, pads, auto_pad):
+    p = L.ConvParams(L._i64arr(strides, 2), L._i64arr(pads, 4), L._i64arr((0, 0), 2), 0, auto_pad, 0)
+    y = (C.c_int64 * 4)()
+    rc = L.lib().b200_conv2d_out_dims(L._i64arr(x), L._i64arr(w), C.byref(p), y)
+    return rc, tuple(y)
+
+
+def test_geometry_matches_oracle():
+    """Host-side shape inference == the oracle's (convolution_op.rs:293-324, max_pool_op.rs:215-246)."""
+    from oracle import ref_ops as R
+    rng = np.random.default_rng(0)
+    n_ok = 0
+    for _ in range(300):
+        H, W = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        kh, kw = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+        sh, sw = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        ap = int(rng.integers(0, 4))
+        pads = [int(v) for v in rng.integers(0, 3, 4)] if ap == 3 else [0, 0, 0, 0]
+        x = np.zeros((1, H, W), np.float32); w = np.zeros((2, 1, kh, kw), np.float32)
+        try:
+            want = R.conv2d_image(x, w, None, ap, pads, (sh, sw)).shape
+        except R.RefPanic:
+            want = None
+        rc, got = _conv_dims((1, 1, H, W), (2, 1, kh, kw), (sh, sw), pads, ap)
+        if want is None:
+            assert rc != 0, (H, W, kh, kw, sh, sw, ap, pads)
+        else:
+            assert rc == 0 and got == (1, 2) + want[1:], (H, W, kh, kw, sh, sw, ap, pads, got, want)
+            n_ok += 1
+        pp = L.PoolParams(L._i64arr((kh, kw), 2), L._i64arr((sh, sw), 2), L._i64arr(pads, 4), ap, 0)
+        y = (C.c_int64 * 4)()
+        rc = L.lib().b200_maxpool2d_out_dims(L._i64arr((1, 1, H, W)), C.byref(pp), y)
+        try:
+            wantp = R.maxpool_image(x, (kh, kw), ap, pads, (sh, sw)).shape
+        except R.RefPanic:
+            wantp = None
+        if wantp is None:
+            assert rc != 0
+        else:
+            assert rc == 0 and tuple(y) == (1, 1) + wantp[1:]
+    assert n_ok > 100
+
+
+def test_reference_panics_become_error_codes():
+    rc, _ = _conv_dims((1, 1, 8, 8), (2, 1, 3, 3), (0, 0), (0, 0, 0, 0), 0)     # strides missing (convolution_op.rs:285)
+    assert rc == -1 and b"strides" in L.lib().b200_last_error()
+    rc, _ = _conv_dims((1, 3, 8, 8), (2, 1, 3, 3), (1, 1), (0, 0, 0, 0), 0)     # C mismatch (convolution_op.rs:252)
+    assert rc == -1
+    rc, got = _conv_dims((1, 1, 8, 8), (2, 1, 3, 3), (1, 1), (1, 1, 1, 1), 0)   # pad promotion VALID -> NOTSET (:169-173)
+    assert rc == 0 and got == (1, 2, 8, 8)
+    pp = L.PoolParams(L._i64arr((3, 3), 2), L._i64arr((2, 2), 2), L._i64arr((0, 0, 1, 1), 4), 0, 0)
+    y = (C.c_int64 * 4)()
+    assert L.lib().b200_maxpool2d_out_dims(L._i64arr((1, 4, 54, 54)), C.byref(pp), y) == 0
+    assert tuple(y) == (1, 4, 26, 26)                                             # pads ignored without NOTSET
+    pp.auto_pad = 3
+    assert L.lib().b200_maxpool2d_out_dims(L._i64arr((1, 4, 54, 54)), C.byref(pp), y) == 0
+    assert tuple(y) == (1, 4, 27, 27)
