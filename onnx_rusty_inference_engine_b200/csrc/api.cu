@@ -1,6 +1,7 @@
 // C ABI: library, context, tensors and the ten operator entry points (include/b200rt.h).
 // Each operator mirrors one function of src/inference_fp32_ops/*.rs (cited in the header) and launches the
 // hand-written kernels of this directory; nothing here computes on the host.
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -337,7 +338,9 @@ int b200_conv2d(b200_ctx* ctx, const b200_tensor* x, const b200_tensor* w, const
   a.y = (*y)->v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = (*y)->v.ld;
   a.sh = (int)p->strides[0]; a.sw = (int)p->strides[1]; a.pt = g.pt; a.pl = g.pl;
   a.relu = p->fuse_relu ? 1 : 0;
-  if (tc_supported(a) == 0) {
+  // B200_CONV_PATH=1 forces the CUDA-core cross-check kernel for the per-op entry point (tests / debugging)
+  static const int forced_path = [] { const char* e = getenv("B200_CONV_PATH"); return e ? atoi(e) : 0; }();
+  if (forced_path != 1 && tc_supported(a) == 0) {
     b200_tensor* wm = const_cast<b200_tensor*>(w);
     if (!wm->tc) { B200_TRY(tc_prepare_weights(a.w, a.M, a.K, ctx->stream, &wm->tc)); ctx->launches++; }
     B200_TRY(launch_conv_tc(a, *wm->tc, ctx->stream));
