@@ -1,23 +1,27 @@
-// tcgen05 3xTF32 implicit-GEMM convolution for sm_100a.
+// tcgen05 3xTF32 implicit-GEMM convolution for sm_100a -- persistent, warp-specialised.
 //
 // Semantics: conv2d, convolution_op.rs:224-517 (+ folded Add add_op.rs:75 and Relu relu_op.rs:31-33), identical to
-// conv_simt.cu; fp32 accuracy is kept by splitting every operand x into hi = tf32(x) (top 19 bits) and
-// lo = x - hi and issuing three tensor-core products per k-step, lo*hi + hi*lo + hi*hi, into one fp32 TMEM
-// accumulator (the lo*lo term is below fp32 rounding).
+// conv_simt.cu.  fp32 accuracy is kept by splitting every operand x into hi = rna_tf32(x) and lo = rna_tf32(x - hi)
+// and issuing three tensor-core products per k-step: hi*hi into a main accumulator, lo*hi + hi*lo into a separate
+// correction accumulator (the tensor core truncates when it folds products into the fp32 accumulator; keeping the
+// 2^-11-times smaller terms apart costs no extra MMAs and removes two thirds of the truncation steps from the main
+// sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.
 //
 // GEMM view: D[P x M] = A[P x K] * W[M x K]^T, P = N*Ho*Wo output pixels, K = KH*KW*C ordered (r, s, c).
-//   UMMA tile: 128 pixels (TMEM lanes) x BN output channels (TMEM columns, two accumulators: main and correction), k-block = 32 floats = one 128-byte
-//   swizzle row, 4 k-steps of 8 per block, kind::tf32, cta_group::1, both operands K-major in shared memory.
-// Warp roles (192 threads):
-//   warps 0-3  A producers: gather the im2col rows straight from the channels-last activation (any stride /
-//              padding / tap, 16-byte chunks), split hi/lo in registers, store both tiles in the 128B-swizzled
-//              K-major layout UMMA expects, fence.proxy.async, arrive.  After the main loop the same warps run the
-//              epilogue: tcgen05.ld the accumulator rows, + bias (+ channel add), Relu, store at the
-//              (channel-offset) destination.
-//   warp 4     allocates TMEM, initialises the mbarriers and issues the TMA loads of the pre-split weight tiles
-//              (cp.async.bulk.tensor.2d, SWIZZLE_128B) -- weights are split and padded ONCE per model.
-//   warp 5     one thread issues tcgen05.mma and tcgen05.commit (frees the stage / signals the epilogue).
-// Pipeline: S stages of {A_hi, A_lo, B_hi, B_lo}; full_a / full_b / empty mbarriers per stage.
+//   UMMA tile 128 pixels (TMEM lanes) x BN <= 128 output channels (TMEM columns), k-block = 32 floats = one 128-byte
+//   swizzle row = 4 k-steps of 8, kind::tf32, cta_group::1, both operands K-major in shared memory.
+//   TMEM: 2 accumulator stages x {main, correction} x BN columns (<= 512), so the epilogue of tile i overlaps the
+//   main loop of tile i+1.
+// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 14 warps:
+//   warps 0-3   epilogue: tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..), + bias (+ channel add), Relu,
+//               transpose 32 rows x 32 channels through swizzled shared memory and write complete 128-byte row
+//               segments at the (channel-offset) destination.
+//   warp 4      allocates TMEM, initialises mbarriers, issues the TMA loads of the pre-split weight tiles.
+//   warp 5      one thread issues tcgen05.mma / tcgen05.commit.
+//   warps 6-13  A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
+//               tap; 16-byte chunks; 4 k-blocks of loads in flight per thread), split hi/lo in registers, store both
+//               tiles in the 128B-swizzled K-major layout UMMA expects, fence.proxy.async, arrive.
+// Weights are split, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
 #include <cuda.h>
 
 #include "internal.h"
@@ -33,21 +37,31 @@ struct TcWeights {
 
 namespace {
 
-constexpr int BM = 128;          // pixels per tile (UMMA M)
-constexpr int BK = 32;           // floats per k-block (128 bytes)
+constexpr int BM = 128;                    // pixels per tile (UMMA M)
+constexpr int BK = 32;                     // floats per k-block (128 bytes)
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
-constexpr int NTHREADS = 192;
-constexpr int SMEM_BUDGET_2CTA = 112 * 1024;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int PROD_WARP0 = 6;
+constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 448
+constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 4 rows per producer thread per k-block
+constexpr int PREFETCH = 4;                // k-blocks of A loads in flight per producer thread
+constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 channels
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_SLAB_BYTES;  // 16 KB
 constexpr int SMEM_MAX = 227 * 1024;
+constexpr int MAX_STAGES = 6;
 
 struct TcParams {
   ConvArgs a;
-  int BN;        // output channels per tile (multiple of 16, <= 256)
-  int S;         // pipeline stages
-  int nkb;       // k-blocks
-  int tmem_cols; // power of two >= max(32, 2*BN): main accumulator + correction accumulator
-  int Mpad;      // weight rows per half (hi / lo)
-  int vec_store; // destination allows 16-byte stores
+  int BN;          // output channels per tile (multiple of 16, <= 128)
+  int S;           // smem pipeline stages
+  int nkb;         // k-blocks per tile
+  int n_tiles_n;   // channel tiles
+  int total_tiles; // pixel tiles x channel tiles
+  int tmem_cols;   // power of two >= 4*BN
+  int Mpad;        // weight rows per half (hi / lo)
+  int P;           // output pixels (fits in int32, checked on the host)
+  int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -85,7 +99,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -138,32 +151,42 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const ConvArgs& a = p.a;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.BN * BK * 4;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-  const uint32_t bars = smem_base + (uint32_t)p.S * stage_bytes;      // 8-byte mbarriers
+  const uint32_t epi_staging = smem_base + (uint32_t)p.S * stage_bytes;          // 2 KB-aligned slabs
+  const uint32_t sbias = epi_staging + EPI_STAGING_BYTES;                        // Mpad floats: bias, zero padded
+  const uint32_t sadd = sbias + 4u * (uint32_t)p.Mpad;                           // Mpad floats: folded channel add
+  const uint32_t bars = sadd + 4u * (uint32_t)p.Mpad;                            // 8-byte mbarriers
   auto full_a = [&](int s) { return bars + 8u * s; };
-  auto full_b = [&](int s) { return bars + 8u * (p.S + s); };
-  auto empty = [&](int s) { return bars + 8u * (2 * p.S + s); };
-  const uint32_t mma_done = bars + 8u * (3 * p.S);
-  const uint32_t tmem_slot = mma_done + 8u;
+  auto full_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (3 * MAX_STAGES + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (3 * MAX_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (3 * MAX_STAGES + 4);
   auto a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
   auto b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES; };
   auto b_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES + b_tile_bytes; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long P = (long long)a.N * a.Ho * a.Wo;
-  const long long p0 = (long long)blockIdx.x * BM;
-  const int m0 = blockIdx.y * p.BN;
+
+  // per-channel epilogue constants -> shared memory once per CTA (the epilogue then needs no global loads)
+  for (int m = threadIdx.x; m < p.Mpad; m += NTHREADS) {
+    const float b = (a.bias && m < a.M) ? __ldg(a.bias + m) : 0.f;
+    const float c = (a.chan_add && m < a.M) ? __ldg(a.chan_add + m) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sbias + 4u * m), "f"(b) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sadd + 4u * m), "f"(c) : "memory");
+  }
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), 4); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-      mbar_init(mma_done, 1);
+      for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -175,137 +198,228 @@ __global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp < 4) {
-    // ================================================================ A producers
+  if (warp >= PROD_WARP0) {
+    // ================================================================ A producers (8 warps)
+    const int pw = warp - PROD_WARP0;
     const int chunk = lane & 7;      // 16-byte chunk within the 128-byte k-block row
     const int rsub = lane >> 3;      // 4 rows per warp-wide access
-    long long pix_base[8];
-    int hw0[8];                      // (h0 << 16) | (w0 & 0xffff), both may be negative (padding)
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) ++my_tiles;
+    const int items = my_tiles * p.nkb;
+
+    // ---- load cursor: (tile, k-block) of the next loads to issue, with that tile's row geometry
+    int l_tile = blockIdx.x, l_kb = 0;
+    int pix_base[ROWS_PER_THREAD];   // n*H*W (fits int32: checked on the host)
+    int hw0[ROWS_PER_THREAD];        // (h0 << 16) | (w0 & 0xffff); both may be negative (padding)
     uint32_t valid = 0;
+    auto set_tile = [&](int tile) {
+      const int p0 = (tile / p.n_tiles_n) * BM;
+      valid = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = warp * 32 + i * 4 + rsub;
-      const long long pp = p0 + row;
-      const bool ok = pp < P;
-      const long long q = ok ? pp : 0;
-      const int wo = (int)(q % a.Wo);
-      const long long t = q / a.Wo;
-      const int ho = (int)(t % a.Ho);
-      const long long n = t / a.Ho;
-      pix_base[i] = n * a.H * a.W;
-      const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
-      hw0[i] = (h0 << 16) | (w0 & 0xFFFF);
-      valid |= (ok ? 1u : 0u) << i;
-    }
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int s = kb % p.S;
-      const uint32_t ph = (uint32_t)(kb / p.S) & 1u;
-      const int k = kb * BK + chunk * 4;
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        const int row = pw * 16 + i * 4 + rsub;
+        const int pp = p0 + row;
+        const bool ok = pp < p.P;
+        const int q = ok ? pp : 0;
+        const int wo = q % a.Wo;
+        const int t = q / a.Wo;
+        const int ho = t % a.Ho;
+        const int n = t / a.Ho;
+        pix_base[i] = n * a.H * a.W;
+        const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
+        hw0[i] = (h0 << 16) | (w0 & 0xFFFF);
+        valid |= (ok ? 1u : 0u) << i;
+      }
+    };
+    float4 v[PREFETCH][ROWS_PER_THREAD];
+    auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
+      const int k = l_kb * BK + chunk * 4;
       const int tap = k / a.C;
       const int c = k - tap * a.C;
       const int r = tap / a.KW, sx = tap - r * a.KW;
       const bool kvalid = k < a.K;
-      float4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
         const int h = (hw0[i] >> 16) + r;
         const int w = (int)(short)(hw0[i] & 0xFFFF) + sx;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kvalid && ((valid >> i) & 1u) && h >= 0 && h < a.H && w >= 0 && w < a.W)
-          v[i] = __ldg(reinterpret_cast<const float4*>(a.x + (pix_base[i] + (long long)h * a.W + w) * a.ldx + c));
+          dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (long long)(pix_base[i] + h * a.W + w) * a.ldx + c));
       }
-      mbar_wait(empty(s), ph ^ 1u);
-      const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
+      if (++l_kb == p.nkb) {
+        l_kb = 0;
+        l_tile += gridDim.x;
+        if (l_tile < p.total_tiles) set_tile(l_tile);
+      }
+    };
+    if (items > 0) set_tile(l_tile);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = warp * 32 + i * 4 + rsub;
-        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        float4 hi, lo;
-        hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
-        lo.x = tf32_rna(v[i].x - hi.x); lo.y = tf32_rna(v[i].y - hi.y); lo.z = tf32_rna(v[i].z - hi.z); lo.w = tf32_rna(v[i].w - hi.w);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-      }
-      fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_a(s));
-    }
+    for (int d = 0; d < PREFETCH; ++d)
+      if (d < items) issue(v[d]);
 
-    // ================================================================ epilogue (same 4 warps: TMEM lanes 32*warp ..)
-    mbar_wait(mma_done, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const long long pp = p0 + row;
-    float* yrow = a.y + pp * a.ldy;
-    for (int j0 = 0; j0 < p.BN; j0 += 16) {
-      uint32_t acc[16], cor[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)j0, acc);
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(p.BN + j0), cor);
-      tmem_ld_wait();
-      if (pp < P) {
-        float o[16];
+    int s = 0;
+    uint32_t ph = 0;
+    for (int base = 0; base < items; base += PREFETCH) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int m = m0 + j0 + j;
-          float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);  // hi*hi + (lo*hi + hi*lo)
-          if (m < a.M) {
-            if (a.bias) val = val + __ldg(a.bias + m);          // add_bias, convolution_op.rs:705
-            if (a.chan_add) val = val + __ldg(a.chan_add + m);  // folded Add node, add_op.rs:75
-            if (a.relu) val = fmaxf(val, 0.f);
+      for (int d = 0; d < PREFETCH; ++d) {
+        const int idx = base + d;
+        if (idx < items) {
+          mbar_wait(empty(s), ph ^ 1u);
+          const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            const int row = pw * 16 + i * 4 + rsub;
+            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+            const float4 x = v[d][i];
+            float4 hi, lo;
+            hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+            lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
           }
-          o[j] = val;
-        }
-        if (p.vec_store && m0 + j0 + 16 <= a.M) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(yrow + m0 + j0 + q * 4) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (m0 + j0 + j < a.M) yrow[m0 + j0 + j] = o[j];
+          // No proxy fence here: a fence in this thread would also wait for the PREFETCH-1 k-blocks of global
+          // loads it still has in flight and serialise the pipeline.  The stores are released by the mbarrier
+          // arrive below; the MMA thread acquires them with its wait on full_a and issues the generic->async
+          // proxy fence itself, immediately before the tcgen05.mma that reads this stage.
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full_a(s));
+          if (idx + PREFETCH < items) issue(v[d]);
+          if (++s == p.S) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 4) {
     // ================================================================ weight tiles via TMA
     if (lane == 0) {
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % p.S;
-        const uint32_t ph = (uint32_t)(kb / p.S) & 1u;
-        mbar_wait(empty(s), ph ^ 1u);
-        mbar_expect_tx(full_b(s), 2u * (uint32_t)b_tile_bytes);
-        tma_load_2d(b_hi(s), &tmapB, full_b(s), kb * BK, m0);
-        tma_load_2d(b_lo(s), &tmapB, full_b(s), kb * BK, p.Mpad + m0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int m0 = (t % p.n_tiles_n) * p.BN;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full_b(s), 2u * (uint32_t)b_tile_bytes);
+          tma_load_2d(b_hi(s), &tmapB, full_b(s), kb * BK, m0);
+          tma_load_2d(b_lo(s), &tmapB, full_b(s), kb * BK, p.Mpad + m0);
+          if (++s == p.S) { s = 0; ph ^= 1u; }
+        }
       }
     }
-  } else {
+  } else if (warp == 5) {
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32(p.BN);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % p.S;
-        const uint32_t ph = (uint32_t)(kb / p.S) & 1u;
-        mbar_wait(full_a(s), ph);
-        mbar_wait(full_b(s), ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int tc = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
+        const int as = tc & 1;
+        const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
+        mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const int ksteps = min(4, (a.K - kb * BK + 7) >> 3);
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t ah = smem_desc_sw128(a_hi(s) + kk * 32);
-          const uint64_t al = smem_desc_sw128(a_lo(s) + kk * 32);
-          const uint64_t bh = smem_desc_sw128(b_hi(s) + kk * 32);
-          const uint64_t bl = smem_desc_sw128(b_lo(s) + kk * 32);
-          // The tensor core truncates when it folds products into the fp32 accumulator, so the main term and the
-          // 2^-11-times smaller correction terms get separate accumulators (columns [0,BN) and [BN,2BN)) and are
-          // added once, in the epilogue: the correction sum then loses nothing and the main sum sees 1/3 of the
-          // accumulation steps.
-          const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-          umma_tf32(tmem_base + (uint32_t)p.BN, al, bh, idesc, acc);
-          umma_tf32(tmem_base + (uint32_t)p.BN, ah, bl, idesc, 1u);
-          umma_tf32(tmem_base, ah, bh, idesc, acc);
+        const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
+        const uint32_t d_corr = d_main + (uint32_t)p.BN;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_a(s), ph);   // acquire: the producers' st.shared of this stage are visible to this thread
+          fence_proxy_async();        // ... and ordered before the async-proxy reads of the MMAs issued below
+          mbar_wait(full_b(s), ph);
+          tc_fence_after();
+          const int ksteps = min(4, (a.K - kb * BK + 7) >> 3);
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t ah = smem_desc_sw128(a_hi(s) + kk * 32);
+            const uint64_t al = smem_desc_sw128(a_lo(s) + kk * 32);
+            const uint64_t bh = smem_desc_sw128(b_hi(s) + kk * 32);
+            const uint64_t bl = smem_desc_sw128(b_lo(s) + kk * 32);
+            const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
+            umma_tf32(d_corr, al, bh, idesc, acc);
+            umma_tf32(d_corr, ah, bl, idesc, 1u);
+            umma_tf32(d_main, ah, bh, idesc, acc);
+          }
+          umma_commit(empty(s));   // frees the smem stage once the MMAs above have read it
+          if (++s == p.S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(empty(s));   // frees the stage when the MMAs above have read it
+        umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
       }
-      umma_commit(mma_done);     // accumulator complete -> epilogue
+    }
+  } else {
+    // ================================================================ epilogue (warps 0-3: TMEM lanes 32*warp ..)
+    // Each warp drains its 32 accumulator rows 32 channels at a time: registers -> a 32 x 128-byte swizzled slab in
+    // shared memory (row-per-thread writes, conflict-free) -> read back with 8 lanes per row so that every global
+    // store instruction writes four complete 128-byte row segments of the channels-last destination.
+    const uint32_t slab = epi_staging + (uint32_t)warp * EPI_SLAB_BYTES;
+    const bool has_add = a.chan_add != nullptr, do_relu = a.relu != 0;
+    int tc = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
+      const int as = tc & 1;
+      const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
+      const int p0 = (t / p.n_tiles_n) * BM;
+      const int m0 = (t % p.n_tiles_n) * p.BN;
+      mbar_wait(tmem_full(as), aph);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * 2 * p.BN);
+      for (int j0 = 0; j0 < p.BN; j0 += 32) {
+        const int width = min(32, p.BN - j0);   // 32, or 16 for the last group when BN % 32 == 16
+        for (int h = 0; h < width; h += 16) {
+          uint32_t acc[16], cor[16];
+          tmem_ld16(t_main + (uint32_t)(j0 + h), acc);
+          tmem_ld16(t_main + (uint32_t)(p.BN + j0 + h), cor);
+          tmem_ld_wait();
+          float o[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 b4, c4;
+            const uint32_t off = 4u * (uint32_t)(m0 + j0 + h + q * 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + off));
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (has_add) {
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + off));
+              cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 4 + e;
+              float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
+              val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
+              if (has_add) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
+              if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
+              o[j] = val;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = (h >> 2) + q;   // 16-byte chunk within the 128-byte slab row
+            const uint32_t addr = slab + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[q * 4]), "f"(o[q * 4 + 1]), "f"(o[q * 4 + 2]), "f"(o[q * 4 + 3]) : "memory");
+          }
+        }
+        __syncwarp();
+        const int c = lane & 7;
+        const int m = m0 + j0 + c * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);
+          const int prow = p0 + warp * 32 + rr;
+          if (c * 4 < width && prow < p.P && m < a.M) {
+            float4 val;
+            const uint32_t addr = slab + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
+            float* dst = a.y + (long long)prow * a.ldy + m;
+            if (p.vec_store && m + 4 <= a.M) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              dst[0] = val.x;
+              if (m + 1 < a.M) dst[1] = val.y;
+              if (m + 2 < a.M) dst[2] = val.z;
+              if (m + 3 < a.M) dst[3] = val.w;
+            }
+          }
+        }
+        __syncwarp();   // the slab is rewritten by the next channel group
+      }
+      // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(as));
     }
   }
 
@@ -348,9 +462,11 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// BN: the smallest multiple of 16 that covers M in ceil(M / 128) channel tiles.
 int pick_bn(int M) {
-  int bn = (M + 15) & ~15;
-  return bn > 256 ? 256 : bn;
+  const int nt = (M + 127) / 128;
+  const int per = (M + nt - 1) / nt;
+  return (per + 15) & ~15;
 }
 
 }  // namespace
@@ -360,6 +476,8 @@ int tc_supported(const ConvArgs& a) {
   if ((((uintptr_t)a.x) & 15) != 0) return B200_EUNSUPPORTED;
   if (a.M < 1 || a.K < 8) return B200_EUNSUPPORTED;
   if (a.H >= 32768 || a.W >= 32768) return B200_EUNSUPPORTED;  // (h0, w0) are packed in 16 bits each
+  const long long P = (long long)a.N * a.Ho * a.Wo, in_pix = (long long)a.N * a.H * a.W;
+  if (P >= (1ll << 31) - BM || in_pix >= (1ll << 31)) return B200_EUNSUPPORTED;  // 32-bit pixel indices in the producer
   return 0;
 }
 
@@ -397,25 +515,34 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.BN = w.BN;
   p.Mpad = w.Mpad;
   p.nkb = w.Kpad / BK;
+  p.P = (int)P;
+  p.n_tiles_n = w.Mpad / w.BN;
+  const long long tiles = ((P + BM - 1) / BM) * p.n_tiles_n;
+  if (tiles >= (1ll << 31)) B200_FAIL(B200_EUNSUPPORTED, "too many tiles");
+  p.total_tiles = (int)tiles;
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.BN) p.tmem_cols <<= 1;   // main + correction accumulators
+  while (p.tmem_cols < 4 * p.BN) p.tmem_cols <<= 1;   // 2 stages x (main + correction)
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * BK * 4;
-  int S = SMEM_BUDGET_2CTA / stage_bytes;
-  if (S < 2) S = 2;
-  if (S > 4) S = 4;
-  if (S > p.nkb) S = p.nkb;
+  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (3 * MAX_STAGES + 5);
+  int S = (SMEM_MAX - fixed) / stage_bytes;
+  if (S > MAX_STAGES) S = MAX_STAGES;
+  if (S < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 stages (BN=%d)", p.BN);
   p.S = S;
+  const size_t smem = (size_t)S * stage_bytes + fixed;
+
   p.vec_store = (a.ldy % 4 == 0 && (((uintptr_t)a.y) & 15) == 0) ? 1 : 0;
-  const size_t smem = (size_t)S * stage_bytes + 1024 + 8 * (3 * S + 2);
-  if (smem > (size_t)SMEM_MAX) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv needs %zu bytes of shared memory", smem);
+
   static bool attr_set[64] = {false};
   int dev = 0;
   B200_CUDA(cudaGetDevice(&dev));
+  static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
     B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)(w.Mpad / w.BN));
+  const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(w.tmap, p);
   B200_CUDA(cudaGetLastError());
   return 0;
