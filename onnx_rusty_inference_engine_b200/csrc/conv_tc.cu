@@ -12,17 +12,20 @@
 //   swizzle row = 4 k-steps of 8, kind::tf32, cta_group::1, both operands K-major in shared memory.
 //   TMEM: 2 accumulator stages x {main, correction} x BN columns (<= 512), so the epilogue of tile i overlaps the
 //   main loop of tile i+1.
-// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 14 warps:
+// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 23 warps:
 //   warps 0-3   epilogue: tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..), + bias (+ channel add), Relu,
 //               transpose 32 rows x 32 channels through swizzled shared memory and write complete 128-byte row
 //               segments at the (channel-offset) destination.
 //   warp 4      allocates TMEM, initialises mbarriers, issues the TMA loads of the pre-split weight tiles.
 //   warp 5      one thread issues tcgen05.mma / tcgen05.commit.
-//   warps 6-13  A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
+//   warp 6      proxy-fence relay (see below)
+//   warps 7-22  A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
 //               tap; 16-byte chunks; 4 k-blocks of loads in flight per thread), split hi/lo in registers, store both
 //               tiles in the 128B-swizzled K-major layout UMMA expects, fence.proxy.async, arrive.
 // Weights are split, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -41,10 +44,11 @@ constexpr int BM = 128;                    // pixels per tile (UMMA M)
 constexpr int BK = 32;                     // floats per k-block (128 bytes)
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int NUM_PROD_WARPS = 8;
-constexpr int PROD_WARP0 = 6;
-constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 448
-constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 4 rows per producer thread per k-block
+constexpr int NUM_PROD_WARPS = 16;
+constexpr int FENCE_WARP = 6;
+constexpr int PROD_WARP0 = 7;
+constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 736
+constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 2 rows per producer thread per k-block
 constexpr int PREFETCH = 4;                // k-blocks of A loads in flight per producer thread
 constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 channels
 constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_SLAB_BYTES;  // 16 KB
@@ -62,6 +66,8 @@ struct TcParams {
   int Mpad;        // weight rows per half (hi / lo)
   int P;           // output pixels (fits in int32, checked on the host)
   int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
+  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores
+  uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -165,9 +171,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   auto full_a = [&](int s) { return bars + 8u * s; };
   auto full_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
   auto empty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
-  auto tmem_full = [&](int s) { return bars + 8u * (3 * MAX_STAGES + s); };
-  auto tmem_empty = [&](int s) { return bars + 8u * (3 * MAX_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bars + 8u * (3 * MAX_STAGES + 4);
+  auto ready_a = [&](int s) { return bars + 8u * (3 * MAX_STAGES + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (4 * MAX_STAGES + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (4 * MAX_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (4 * MAX_STAGES + 4);
   auto a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
   auto b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES; };
@@ -185,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+      for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); mbar_init(ready_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
       fence_barrier_init();
     }
@@ -199,7 +206,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp >= PROD_WARP0) {
-    // ================================================================ A producers (8 warps)
+    // ================================================================ A producers (16 warps)
+    // Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, a base pointer (tap (0,0), channel 0) and two
+    // separable validity masks (bit 16*i+r: input row h0+r inside the image; bit 16*i+s: column w0+s inside).
+    // Per k-block the chunk's (r, s, c) is decoded once (multiply-high division) into one element offset shared by
+    // all rows, so a load costs an add, a mask test and the LDG.
     const int pw = warp - PROD_WARP0;
     const int chunk = lane & 7;      // 16-byte chunk within the 128-byte k-block row
     const int rsub = lane >> 3;      // 4 rows per warp-wide access
@@ -207,44 +218,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) ++my_tiles;
     const int items = my_tiles * p.nkb;
 
-    // ---- load cursor: (tile, k-block) of the next loads to issue, with that tile's row geometry
-    int l_tile = blockIdx.x, l_kb = 0;
-    int pix_base[ROWS_PER_THREAD];   // n*H*W (fits int32: checked on the host)
-    int hw0[ROWS_PER_THREAD];        // (h0 << 16) | (w0 & 0xffff); both may be negative (padding)
-    uint32_t valid = 0;
+    int l_tile = blockIdx.x, l_kb = 0;   // load cursor
+    const float* base[ROWS_PER_THREAD];
+    uint32_t hmask = 0, wmask = 0;
     auto set_tile = [&](int tile) {
+      // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
+      // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
       const int p0 = (tile / p.n_tiles_n) * BM;
-      valid = 0;
+      const int t0 = p0 / a.Wo, wo0 = p0 - t0 * a.Wo;
+      const int n0 = t0 / a.Ho, ho0 = t0 - n0 * a.Ho;
+      hmask = 0; wmask = 0;
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int row = pw * 16 + i * 4 + rsub;
-        const int pp = p0 + row;
-        const bool ok = pp < p.P;
-        const int q = ok ? pp : 0;
-        const int wo = q % a.Wo;
-        const int t = q / a.Wo;
-        const int ho = t % a.Ho;
-        const int n = t / a.Ho;
-        pix_base[i] = n * a.H * a.W;
+        const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
+        const bool ok = p0 + row < p.P;
+        const int wsum = wo0 + row;
+        const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
+        const int wo = wsum - cw * a.Wo;
+        const int hsum = ho0 + cw;
+        const int ch = p.magicHo ? (int)__umulhi((unsigned)hsum, p.magicHo) : hsum;   // hsum / Ho
+        const int ho = hsum - ch * a.Ho;
+        const int n = n0 + ch;
         const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
-        hw0[i] = (h0 << 16) | (w0 & 0xFFFF);
-        valid |= (ok ? 1u : 0u) << i;
+        base[i] = a.x + ((long long)n * a.H * a.W + (long long)h0 * a.W + w0) * a.ldx;
+        // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
+        const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
+        const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
+        const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
+        const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
+        hmask |= hm << (16 * i);
+        wmask |= wm << (16 * i);
       }
     };
     float4 v[PREFETCH][ROWS_PER_THREAD];
     auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
       const int k = l_kb * BK + chunk * 4;
-      const int tap = k / a.C;
+      const int tap = p.magicC ? (int)__umulhi((unsigned)k, p.magicC) : k;      // k / C
       const int c = k - tap * a.C;
-      const int r = tap / a.KW, sx = tap - r * a.KW;
-      const bool kvalid = k < a.K;
+      const int r = p.magicKW ? (int)__umulhi((unsigned)tap, p.magicKW) : tap;  // tap / KW
+      const int sx = tap - r * a.KW;
+      const int delta = (r * a.W + sx) * a.ldx + c;
+      const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 16*i: row i valid for this tap
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int h = (hw0[i] >> 16) + r;
-        const int w = (int)(short)(hw0[i] & 0xFFFF) + sx;
         dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kvalid && ((valid >> i) & 1u) && h >= 0 && h < a.H && w >= 0 && w < a.W)
-          dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (long long)(pix_base[i] + h * a.W + w) * a.ldx + c));
+        if (((m >> (16 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
       }
       if (++l_kb == p.nkb) {
         l_kb = 0;
@@ -257,25 +275,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
     for (int d = 0; d < PREFETCH; ++d)
       if (d < items) issue(v[d]);
 
+    // smem offsets of this thread's rows inside a tile (fixed for the whole kernel)
+    uint32_t soff[ROWS_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+      const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
+      soff[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+    }
     int s = 0;
     uint32_t ph = 0;
-    for (int base = 0; base < items; base += PREFETCH) {
+    for (int base_i = 0; base_i < items; base_i += PREFETCH) {
 #pragma unroll
       for (int d = 0; d < PREFETCH; ++d) {
-        const int idx = base + d;
+        const int idx = base_i + d;
         if (idx < items) {
+          // split in registers first (independent of the stage), then wait for the stage and store
+          float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            const float4 x = v[d][i];
+            hi[i].x = tf32_rna(x.x); hi[i].y = tf32_rna(x.y); hi[i].z = tf32_rna(x.z); hi[i].w = tf32_rna(x.w);
+            lo[i].x = tf32_rna(x.x - hi[i].x); lo[i].y = tf32_rna(x.y - hi[i].y);
+            lo[i].z = tf32_rna(x.z - hi[i].z); lo[i].w = tf32_rna(x.w - hi[i].w);
+          }
           mbar_wait(empty(s), ph ^ 1u);
           const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            const int row = pw * 16 + i * 4 + rsub;
-            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-            const float4 x = v[d][i];
-            float4 hi, lo;
-            hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
-            lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + soff[i]), "f"(hi[i].x), "f"(hi[i].y), "f"(hi[i].z), "f"(hi[i].w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + soff[i]), "f"(lo[i].x), "f"(lo[i].y), "f"(lo[i].z), "f"(lo[i].w) : "memory");
           }
           // No proxy fence here: a fence in this thread would also wait for the PREFETCH-1 k-blocks of global
           // loads it still has in flight and serialise the pipeline.  The stores are released by the mbarrier
@@ -297,9 +325,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         const int m0 = (t % p.n_tiles_n) * p.BN;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(empty(s), ph ^ 1u);
+          if (p.debug & 1) { mbar_arrive(full_b(s)); if (++s == p.S) { s = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(full_b(s), 2u * (uint32_t)b_tile_bytes);
           tma_load_2d(b_hi(s), &tmapB, full_b(s), kb * BK, m0);
           tma_load_2d(b_lo(s), &tmapB, full_b(s), kb * BK, p.Mpad + m0);
+          if (++s == p.S) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == FENCE_WARP) {
+    // ================================================================ proxy-fence relay
+    // The A tiles are written with ordinary st.shared (generic proxy) and read by tcgen05.mma (async proxy), so a
+    // fence.proxy.async has to sit between them.  It compiles to MEMBAR.ALL.CTA: in a producer thread it would wait
+    // for that thread's prefetched global loads, in the MMA thread it would wait for the MMAs in flight -- either
+    // way one fence per k-block serialises the pipeline (measured: ~1.8K clk per k-block for every layer).  This
+    // thread has nothing outstanding: it acquires full_a, fences, and releases ready_a to the MMA thread.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_a(s), ph);
+          fence_proxy_async();
+          mbar_arrive(ready_a(s));
           if (++s == p.S) { s = 0; ph ^= 1u; }
         }
       }
@@ -319,8 +367,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
         const uint32_t d_corr = d_main + (uint32_t)p.BN;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(full_a(s), ph);   // acquire: the producers' st.shared of this stage are visible to this thread
-          fence_proxy_async();        // ... and ordered before the async-proxy reads of the MMAs issued below
+          mbar_wait(ready_a(s), ph);  // A stage written, released, and proxy-fenced by the fence warp
           mbar_wait(full_b(s), ph);
           tc_fence_after();
           const int ksteps = min(4, (a.K - kb * BK + 7) >> 3);
@@ -399,7 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + (lane >> 3);
           const int prow = p0 + warp * 32 + rr;
-          if (c * 4 < width && prow < p.P && m < a.M) {
+          if (c * 4 < width && prow < p.P && m < a.M && !(p.debug & 4)) {
             float4 val;
             const uint32_t addr = slab + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) << 4);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
@@ -475,7 +522,10 @@ int tc_supported(const ConvArgs& a) {
   if (a.C % 4 != 0 || a.ldx % 4 != 0 || a.wc != a.C) return B200_EUNSUPPORTED;
   if ((((uintptr_t)a.x) & 15) != 0) return B200_EUNSUPPORTED;
   if (a.M < 1 || a.K < 8) return B200_EUNSUPPORTED;
-  if (a.H >= 32768 || a.W >= 32768) return B200_EUNSUPPORTED;  // (h0, w0) are packed in 16 bits each
+  if (a.KH > 15 || a.KW > 15 || a.pt > 15 || a.pl > 15 || ROWS_PER_THREAD > 2) return B200_EUNSUPPORTED;                  // 16-bit validity masks per row
+  if (a.Ho + BM >= 65536 || a.Wo + BM >= 65536) return B200_EUNSUPPORTED;                       // multiply-high division range
+  if (a.K >= 65536 || a.C >= 65536) return B200_EUNSUPPORTED;                                 // multiply-high division range
+  if ((long long)(a.KH + 1) * a.W * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;           // 32-bit tap offsets
   const long long P = (long long)a.N * a.Ho * a.Wo, in_pix = (long long)a.N * a.H * a.W;
   if (P >= (1ll << 31) - BM || in_pix >= (1ll << 31)) return B200_EUNSUPPORTED;  // 32-bit pixel indices in the producer
   return 0;
@@ -523,7 +573,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 4 * p.BN) p.tmem_cols <<= 1;   // 2 stages x (main + correction)
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * BK * 4;
-  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (3 * MAX_STAGES + 5);
+  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (4 * MAX_STAGES + 5);
   int S = (SMEM_MAX - fixed) / stage_bytes;
   if (S > MAX_STAGES) S = MAX_STAGES;
   if (S < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 stages (BN=%d)", p.BN);
@@ -531,6 +581,11 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   const size_t smem = (size_t)S * stage_bytes + fixed;
 
   p.vec_store = (a.ldy % 4 == 0 && (((uintptr_t)a.y) & 15) == 0) ? 1 : 0;
+  { static const int dbg = [] { const char* e = getenv("B200_TC_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
+  p.magicC = a.C == 1 ? 0u : (uint32_t)(((1ull << 32) + a.C - 1) / a.C);
+  p.magicKW = a.KW == 1 ? 0u : (uint32_t)(((1ull << 32) + a.KW - 1) / a.KW);
+  p.magicWo = a.Wo == 1 ? 0u : (uint32_t)(((1ull << 32) + a.Wo - 1) / a.Wo);
+  p.magicHo = a.Ho == 1 ? 0u : (uint32_t)(((1ull << 32) + a.Ho - 1) / a.Ho);
 
   static bool attr_set[64] = {false};
   int dev = 0;
