@@ -80,37 +80,38 @@ __global__ void add_same_kernel(const float* __restrict__ x, const float* __rest
 
 // ------------------------------------------------------------------ MaxPool (max_pool_op.rs:157-360)
 // Zero-fill padding (:265-276) and a fold that starts at -FLT_MAX (:337).  Thread per (output pixel, 4 channels).
-template <bool VEC>
+template <bool VEC, typename IDX>
 __global__ void maxpool_kernel(PoolArgs a) {
+  // IDX = unsigned (all element counts < 2^31: 32-bit divisions) or long long
   const int CV = VEC ? a.C / 4 : a.C;
-  const long long out_pixels = (long long)a.N * a.Ho * a.Wo;
-  const long long total = out_pixels * CV;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / CV;
+  const IDX out_pixels = (IDX)a.N * a.Ho * a.Wo;
+  const IDX total = out_pixels * CV;
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+    const IDX pix = i / CV;
     const int c = (int)(i - pix * CV);
     const int wo = (int)(pix % a.Wo);
-    const long long t = pix / a.Wo;
+    const IDX t = pix / a.Wo;
     const int ho = (int)(t % a.Ho);
-    const long long n = t / a.Ho;
+    const IDX n = t / a.Ho;
     const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
+    const float* img = a.x + (long long)n * a.H * a.W * a.ldx + (VEC ? c * 4 : c);
     float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
     for (int r = 0; r < a.kh; ++r) {
       const int h = h0 + r;
-      const bool hin = (h >= 0 && h < a.H);
+      const bool hin = (unsigned)h < (unsigned)a.H;
       for (int s = 0; s < a.kw; ++s) {
         const int w = w0 + s;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // padded taps read as 0.0, like the reference
-        if (hin && w >= 0 && w < a.W) {
-          const float* px = a.x + ((n * a.H + h) * a.W + w) * a.ldx;
-          if (VEC) v = ldg4(px + c * 4);
-          else v.x = __ldg(px + c);
+        if (hin && (unsigned)w < (unsigned)a.W) {
+          const float* px = img + (long long)(h * a.W + w) * a.ldx;
+          if (VEC) v = ldg4(px);
+          else v.x = __ldg(px);
         }
         m.x = fmaxf(m.x, v.x);
         if (VEC) { m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w); }
       }
     }
-    float* py = a.y + pix * a.ldy;
+    float* py = a.y + (long long)pix * a.ldy;
     if (VEC) *reinterpret_cast<float4*>(py + c * 4) = m;
     else py[c] = m.x;
   }
@@ -189,17 +190,42 @@ __global__ void softmax_kernel(const float* __restrict__ x, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------ GlobalAveragePool + Softmax fused (SqueezeNet tail)
-// One block per image: channel means into shared memory (coalesced over channels), then the softmax over them.
-__global__ void gap_softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int ldx) {
-  extern __shared__ float mean[];  // C floats
+// One 1024-thread block per image.  Phase 1: thread (g, sl) sums channel group g (4 channels, one 128-bit load per
+// pixel) over pixel slice sl of kGapSlices -- lanes walk consecutive channel groups, so every load instruction reads
+// complete 512-byte runs of one pixel row; the per-thread loads are independent and stay in flight.  Phase 2: the
+// slices are combined in a fixed order, divided by H*W, and the softmax runs over the means in shared memory.
+constexpr int kGapThreads = 1024;
+constexpr int kGapSlices = 4;
+template <bool VEC>
+__global__ void __launch_bounds__(kGapThreads) gap_softmax_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW,
+                                                                  int ldx) {
+  extern __shared__ float sm[];  // [kGapSlices][C] partial sums, then [C] means
   __shared__ float red[32];
+  float* mean = sm + (size_t)kGapSlices * C;
   const long long n = blockIdx.x;
   const float* xin = x + n * HW * (long long)ldx;
+  const int sl = threadIdx.x >> 8;            // pixel slice 0..3
+  const int G = VEC ? C / 4 : C;
+  for (int g = threadIdx.x & 255; g < G; g += 256) {
+    if (VEC) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int k = sl; k < HW; k += kGapSlices) {
+        const float4 v = ldg4(xin + (long long)k * ldx + g * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(sm + (size_t)sl * C + g * 4) = acc;
+    } else {
+      float acc = 0.f;
+#pragma unroll 4
+      for (int k = sl; k < HW; k += kGapSlices) acc += __ldg(xin + (long long)k * ldx + g);
+      sm[(size_t)sl * C + g] = acc;
+    }
+  }
+  __syncthreads();
   float m = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < HW; ++k) s += __ldg(xin + (long long)k * ldx + c);
-    s = s / (float)HW;
+    const float s = ((sm[c] + sm[C + c]) + (sm[2 * C + c] + sm[3 * C + c])) / (float)HW;
     mean[c] = s;
     m = fmaxf(m, s);
   }
@@ -255,10 +281,13 @@ int launch_maxpool(const PoolArgs& a, cudaStream_t st) {
   const long long out_pixels = (long long)a.N * a.Ho * a.Wo;
   if (out_pixels == 0 || a.C == 0) return 0;
   const bool vec = a.C % 4 == 0 && a.ldx % 4 == 0 && a.ldy % 4 == 0 && aligned16(a.x) && aligned16(a.y);
-  if (vec)
-    maxpool_kernel<true><<<grid_for(out_pixels * (a.C / 4), kThreads, 16), kThreads, 0, st>>>(a);
-  else
-    maxpool_kernel<false><<<grid_for(out_pixels * a.C, kThreads, 16), kThreads, 0, st>>>(a);
+  const bool small = out_pixels * a.C < (1ll << 31) && (long long)a.N * a.H * a.W < (1ll << 31);
+  const long long work = out_pixels * (vec ? a.C / 4 : a.C);
+  const int grid = grid_for(work, kThreads, 32);
+  if (vec && small) maxpool_kernel<true, unsigned><<<grid, kThreads, 0, st>>>(a);
+  else if (vec) maxpool_kernel<true, long long><<<grid, kThreads, 0, st>>>(a);
+  else if (small) maxpool_kernel<false, unsigned><<<grid, kThreads, 0, st>>>(a);
+  else maxpool_kernel<false, long long><<<grid, kThreads, 0, st>>>(a);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -280,9 +309,12 @@ int launch_softmax(TView x, float* y, cudaStream_t st) {
 
 int launch_gap_softmax(TView x, float* y, cudaStream_t st) {
   if (x.N == 0 || x.C == 0) return 0;
-  const size_t smem = (size_t)x.C * sizeof(float);
+  const size_t smem = (size_t)(kGapSlices + 1) * x.C * sizeof(float);
   if (smem > 48 * 1024) B200_FAIL(B200_EUNSUPPORTED, "gap_softmax: C=%d too large for the fused tail", x.C);
-  gap_softmax_kernel<<<x.N, kThreads, smem, st>>>(x.p, y, x.C, x.H * x.W, x.ld);
+  if (vec_ok(x))
+    gap_softmax_kernel<true><<<x.N, kGapThreads, smem, st>>>(x.p, y, x.C, x.H * x.W, x.ld);
+  else
+    gap_softmax_kernel<false><<<x.N, kGapThreads, smem, st>>>(x.p, y, x.C, x.H * x.W, x.ld);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,7 +14,26 @@ inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
   return (int)b;
 }
 
-// dst[n][h][w][0..ld) <- src[n][c][h][w]; thread per (pixel, lane): writes coalesced, reads coalesced per plane.
+// dst[n][h][w][0..ld) <- src[n][c][h][w].  Thread per (pixel, 4 lanes): reads are coalesced per channel plane
+// (consecutive threads = consecutive pixels), writes are 128-bit per pixel.  IDX = unsigned when counts fit 31 bits.
+template <typename IDX>
+__global__ void nchw_to_rows_vec4_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, IDX HW, IDX pixels, int ld,
+                                         int lanes4 /* number of 4-lane groups written per pixel */) {
+  const IDX total = pixels * lanes4;
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+    const IDX pix = i % pixels;          // pixel fastest: coalesced plane reads
+    const int q = (int)(i / pixels);
+    const IDX n = pix / HW, hw = pix - n * HW;
+    const float* s = src + ((long long)n * C + q * 4) * HW + hw;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q * 4 + 0 < C) v.x = __ldg(s);
+    if (q * 4 + 1 < C) v.y = __ldg(s + (long long)HW);
+    if (q * 4 + 2 < C) v.z = __ldg(s + 2 * (long long)HW);
+    if (q * 4 + 3 < C) v.w = __ldg(s + 3 * (long long)HW);
+    *reinterpret_cast<float4*>(dst + (long long)pix * ld + q * 4) = v;
+  }
+}
+
 __global__ void nchw_to_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long HW,
                                     long long pixels, int ld, int lanes /* C or ld (zero-filling) */) {
   const long long total = pixels * lanes;
@@ -92,6 +111,18 @@ int launch_nchw_to_rows(const float* src, TView dst, bool zero_pad_lanes, cudaSt
   const long long pixels = dst.pixels();
   if (pixels == 0 || dst.C == 0) return 0;
   const int lanes = zero_pad_lanes ? dst.ld : dst.C;
+  if (lanes % 4 == 0 && dst.ld % 4 == 0 && aligned16(dst.p) && (zero_pad_lanes || dst.C % 4 == 0)) {
+    // 128-bit row writes (the SqueezeNet input: C = 3 stored with a zero 4th lane)
+    const int lanes4 = lanes / 4;
+    const int grid = grid_for(pixels * lanes4, kThreads, 148 * 32);
+    if (pixels * lanes4 < (1ll << 31))
+      nchw_to_rows_vec4_kernel<unsigned><<<grid, kThreads, 0, st>>>(src, dst.p, dst.C, (unsigned)((long long)dst.H * dst.W),
+                                                                   (unsigned)pixels, dst.ld, lanes4);
+    else
+      nchw_to_rows_vec4_kernel<long long><<<grid, kThreads, 0, st>>>(src, dst.p, dst.C, (long long)dst.H * dst.W, pixels, dst.ld, lanes4);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   nchw_to_rows_kernel<<<grid_for(pixels * lanes, kThreads), kThreads, 0, st>>>(
       src, dst.p, dst.C, (long long)dst.H * dst.W, pixels, dst.ld, lanes);
   B200_CUDA(cudaGetLastError());

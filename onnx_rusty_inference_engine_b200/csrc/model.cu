@@ -647,7 +647,7 @@ int Planner::do_gap(size_t i) {
   size_t j;
   const WireNode* c = sole_consumer(n.output[0], &j);
   TView xv = x->v;
-  if (c && c->op_type == "Softmax" && (size_t)xv.C * sizeof(float) <= 48 * 1024) {
+  if (c && c->op_type == "Softmax" && (size_t)xv.C * 5 * sizeof(float) <= 48 * 1024) {
     // SqueezeNet tail: GAP + Softmax in one kernel (global_average_pool_op.rs:33-52 + softmax_op.rs:45-57)
     consumed.insert(j);
     Val y; y.rank = 2; y.dims[0] = x->dims[0]; y.dims[1] = x->dims[1];
