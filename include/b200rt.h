@@ -152,6 +152,11 @@ int b200_model_free(b200_model *m);
 int b200_model_io(const b200_model *m, int64_t in_chw[3], int64_t *out_per_image);
 /* Host-to-host: uploads `batch` images (NCHW, dense), runs, downloads batch*out_per_image floats. */
 int b200_model_run(b200_model *m, const float *host_in, int64_t batch, float *host_out);
+/* Pipelined host-to-host: enqueues H2D (its own copy stream), the run, and D2H (a second copy stream) and returns;
+ * two batches may be in flight, so the H2D of batch i+1 overlaps the compute of batch i.  host_in / host_out should
+ * be pinned and must stay valid until b200_model_sync returns. */
+int b200_model_run_async(b200_model *m, const float *host_in, int64_t batch, float *host_out);
+int b200_model_sync(b200_model *m);
 /* Device-resident: d_in / d_out are device pointers (NCHW dense input, [batch, out_per_image] output)
  * on the context's device; asynchronous on the context's stream. */
 int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float *d_out);

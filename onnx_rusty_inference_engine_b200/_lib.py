@@ -69,6 +69,8 @@ SIGNATURES = {
     "b200_model_io": (C.c_int, [_vp, _i64p, _i64p]),
     "b200_model_run": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "b200_model_run_device": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "b200_model_run_async": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "b200_model_sync": (C.c_int, [_vp]),
     "b200_model_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "b200_model_profile": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "b200_model_launches_per_run": (C.c_int64, [_vp, C.c_int64]),
@@ -313,6 +315,12 @@ class Model:
     def run_raw(self, in_ptr: int, batch: int, out_ptr: int, device: bool) -> None:
         fn = lib().b200_model_run_device if device else lib().b200_model_run
         check(fn(self._h, _vp(in_ptr), int(batch), _vp(out_ptr)))
+
+    def run_async_raw(self, in_ptr: int, batch: int, out_ptr: int) -> None:
+        check(lib().b200_model_run_async(self._h, _vp(in_ptr), int(batch), _vp(out_ptr)))
+
+    def sync(self) -> None:
+        check(lib().b200_model_sync(self._h))
 
     def launches_per_run(self, batch: int) -> int:
         return int(lib().b200_model_launches_per_run(self._h, int(batch)))

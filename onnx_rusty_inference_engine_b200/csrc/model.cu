@@ -92,9 +92,26 @@ struct b200_model {
   int opt_verbose = 0;
   float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
   float* stage_out = nullptr; size_t stage_out_bytes = 0;
+  // pipelined host-to-host runs (b200_model_run_async): two slots, copy streams separate from the compute stream
+  struct Slot {
+    float* in = nullptr; size_t in_bytes = 0;
+    float* out = nullptr; size_t out_bytes = 0;
+    cudaEvent_t in_ready = nullptr, done = nullptr, out_done = nullptr;
+  } slots[2];
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  uint64_t seq = 0;
   ~b200_model() {
     if (stage_in) cudaFree(stage_in);
     if (stage_out) cudaFree(stage_out);
+    for (auto& sl : slots) {
+      if (sl.in) cudaFree(sl.in);
+      if (sl.out) cudaFree(sl.out);
+      if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+      if (sl.done) cudaEventDestroy(sl.done);
+      if (sl.out_done) cudaEventDestroy(sl.out_done);
+    }
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
   }
 };
 
@@ -969,6 +986,65 @@ int b200_model_run(b200_model* m, const float* host_in, int64_t batch, float* ho
   B200_TRY(run_plan(m, p, m->stage_in, m->stage_out));
   B200_CUDA(cudaMemcpyAsync(host_out, m->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200_model_run_async(b200_model* m, const float* host_in, int64_t batch, float* host_out) {
+  if (!m || !host_in || !host_out) B200_FAIL(B200_EINVAL, "NULL argument");
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m, batch, &p));
+  const size_t in_bytes = (size_t)batch * m->in_dims[0] * m->in_dims[1] * m->in_dims[2] * m->in_dims[3] * sizeof(float);
+  const size_t out_bytes = (size_t)batch * p->out_per_image * sizeof(float);
+  if (!m->h2d) {
+    B200_CUDA(cudaStreamCreateWithFlags(&m->h2d, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&m->d2h, cudaStreamNonBlocking));
+    for (auto& sl : m->slots) {
+      B200_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+  }
+  b200_model::Slot& sl = m->slots[m->seq & 1];
+  const bool reused = m->seq >= 2;
+  m->seq++;
+  if (sl.in_bytes < in_bytes || sl.out_bytes < out_bytes) {
+    if (reused) { B200_CUDA(cudaEventSynchronize(sl.out_done)); }   // growing a slot that may still be in flight
+    if (sl.in_bytes < in_bytes) {
+      if (sl.in) cudaFree(sl.in);
+      sl.in = nullptr; sl.in_bytes = 0;
+      if (cudaMalloc((void**)&sl.in, in_bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for input staging", in_bytes); }
+      sl.in_bytes = in_bytes;
+    }
+    if (sl.out_bytes < out_bytes) {
+      if (sl.out) cudaFree(sl.out);
+      sl.out = nullptr; sl.out_bytes = 0;
+      if (cudaMalloc((void**)&sl.out, out_bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for output staging", out_bytes); }
+      sl.out_bytes = out_bytes;
+    }
+  }
+  cudaStream_t st = m->ctx->stream;
+  // H2D of this batch overlaps the compute of the previous one; the slot's previous occupant must have been
+  // consumed (input transform done) and drained (logits copied out) first
+  if (reused) { B200_CUDA(cudaStreamWaitEvent(m->h2d, sl.done, 0)); }
+  B200_CUDA(cudaMemcpyAsync(sl.in, host_in, in_bytes, cudaMemcpyHostToDevice, m->h2d));
+  B200_CUDA(cudaEventRecord(sl.in_ready, m->h2d));
+  B200_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
+  if (reused) { B200_CUDA(cudaStreamWaitEvent(st, sl.out_done, 0)); }
+  B200_TRY(run_plan(m, p, sl.in, sl.out));
+  B200_CUDA(cudaEventRecord(sl.done, st));
+  B200_CUDA(cudaStreamWaitEvent(m->d2h, sl.done, 0));
+  B200_CUDA(cudaMemcpyAsync(host_out, sl.out, out_bytes, cudaMemcpyDeviceToHost, m->d2h));
+  B200_CUDA(cudaEventRecord(sl.out_done, m->d2h));
+  return 0;
+}
+
+int b200_model_sync(b200_model* m) {
+  if (!m) B200_FAIL(B200_EINVAL, "model is NULL");
+  Guard g(m->ctx);
+  B200_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (m->h2d) B200_CUDA(cudaStreamSynchronize(m->h2d));
+  if (m->d2h) B200_CUDA(cudaStreamSynchronize(m->d2h));
   return 0;
 }
 

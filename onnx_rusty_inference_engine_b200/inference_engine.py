@@ -122,6 +122,13 @@ class Engine:
         self.model.run_raw(x.data_ptr(), n, out.data_ptr(), device=True)
         return out
 
+    def run_pinned_async(self, x_host, out_host) -> None:
+        """Pipelined host-to-host (b200_model_run_async): returns immediately; call sync() before reading out_host."""
+        self.model.run_async_raw(x_host.data_ptr(), x_host.shape[0], out_host.data_ptr())
+
+    def sync(self) -> None:
+        self.model.sync()
+
     def run_pinned(self, x_host, out_host) -> None:
         """Host-to-host through the C ABI with caller-provided (ideally pinned) torch CPU tensors."""
         self.model.run_raw(x_host.data_ptr(), x_host.shape[0], out_host.data_ptr(), device=False)

@@ -120,6 +120,21 @@ def test_engine_on_torch_stream(synth_onnx):
         assert np.array_equal(dev.cpu().numpy(), host)
 
 
+def test_async_pipelined_run_matches_sync(synth_onnx):
+    """b200_model_run_async: several batches in flight (H2D / compute / D2H on three streams) == synchronous runs."""
+    import torch
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    eng = Engine(synth_onnx, device=0)
+    xs = [torch.from_numpy(synth.synthetic_batch(3, seed=20 + i)).pin_memory() for i in range(5)]
+    outs = [torch.zeros((3, 1000), dtype=torch.float32).pin_memory() for _ in range(5)]
+    for x, o in zip(xs, outs):
+        eng.run_pinned_async(x, o)
+    eng.sync()
+    for x, o in zip(xs, outs):
+        assert np.array_equal(o.numpy(), eng(x.numpy())), "pipelined result differs from the synchronous run"
+
+
 def test_unknown_op_and_attr_are_errors(ctx):
     """model_inference.rs:158 (unknown op) and convolution_op.rs:160 (unknown attribute) panic upstream; here they
     are B200_EUNSUPPORTED at load time."""
