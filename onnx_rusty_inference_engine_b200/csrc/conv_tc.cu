@@ -12,14 +12,14 @@
 //   swizzle row = 4 k-steps of 8, kind::tf32, cta_group::1, both operands K-major in shared memory.
 //   TMEM: 2 accumulator stages x {main, correction} x BN columns (<= 512), so the epilogue of tile i overlaps the
 //   main loop of tile i+1.
-// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 23 warps:
-//   warps 0-3   epilogue: tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..), + bias (+ channel add), Relu,
+// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 27 warps:
+//   warps 0-7   epilogue (pairs w, w+4 share TMEM lanes 32*(w%4).. and split the channels): tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..), + bias (+ channel add), Relu,
 //               transpose 32 rows x 32 channels through swizzled shared memory and write complete 128-byte row
 //               segments at the (channel-offset) destination.
-//   warp 4      allocates TMEM, initialises mbarriers, issues the TMA loads of the pre-split weight tiles.
-//   warp 5      one thread issues tcgen05.mma / tcgen05.commit.
-//   warp 6      proxy-fence relay (see below)
-//   warps 7-22  A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
+//   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the pre-split weight tiles.
+//   warp 9      one thread issues tcgen05.mma / tcgen05.commit.
+//   warp 10     proxy-fence relay (see below)
+//   warps 11-26 A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
 //               tap; 16-byte chunks; 4 k-blocks of loads in flight per thread), split hi/lo in registers, store both
 //               tiles in the 128B-swizzled K-major layout UMMA expects, fence.proxy.async, arrive.
 // Weights are split, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
@@ -43,15 +43,17 @@ namespace {
 constexpr int BM = 128;                    // pixels per tile (UMMA M)
 constexpr int BK = 32;                     // floats per k-block (128 bytes)
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int TMA_WARP = 8;
+constexpr int MMA_WARP = 9;
 constexpr int NUM_PROD_WARPS = 16;
-constexpr int FENCE_WARP = 6;
-constexpr int PROD_WARP0 = 7;
-constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 736
+constexpr int FENCE_WARP = 10;
+constexpr int PROD_WARP0 = 11;
+constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 864
 constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 2 rows per producer thread per k-block
 constexpr int PREFETCH = 4;                // k-blocks of A loads in flight per producer thread
-constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp: 32 rows x 32 channels
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_SLAB_BYTES;  // 16 KB
+constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp pair: 32 rows x 32 channels
+constexpr int EPI_STAGING_BYTES = 4 * EPI_SLAB_BYTES;  // one slab per warp pair: 16 KB
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 6;
 
@@ -198,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sadd + 4u * m), "f"(c) : "memory");
   }
 
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); mbar_init(ready_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
@@ -324,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == TMA_WARP) {
     // ================================================================ weight tiles via TMA
     if (lane == 0) {
       int s = 0;
@@ -360,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32(p.BN);
@@ -396,11 +398,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
       }
     }
   } else {
-    // ================================================================ epilogue (warps 0-3: TMEM lanes 32*warp ..)
-    // Each warp drains its 32 accumulator rows 32 channels at a time: registers -> a 32 x 128-byte swizzled slab in
-    // shared memory (row-per-thread writes, conflict-free) -> read back with 8 lanes per row so that every global
-    // store instruction writes four complete 128-byte row segments of the channels-last destination.
-    const uint32_t slab = epi_staging + (uint32_t)warp * EPI_SLAB_BYTES;
+    // ================================================================ epilogue (warps 0-7)
+    // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w and w+4 form a pair on the same 32 accumulator
+    // rows and split every 32-channel group: `half` 0 drains channels [j0, j0+16), `half` 1 drains [j0+16, j0+32).
+    // Both write their 16 channels into the pair's shared 32 x 128-byte swizzled slab (row-per-thread, conflict-free),
+    // meet on a 64-thread named barrier, and then each stores 16 of the 32 rows with 8 lanes per row, so that every
+    // global store instruction writes four complete 128-byte row segments of the channels-last destination.
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t slab = epi_staging + (uint32_t)quarter * EPI_SLAB_BYTES;
+    const uint32_t pair_bar = 1u + (uint32_t)quarter;   // named barriers 1..4 (0 is __syncthreads)
     const bool has_add = a.chan_add != nullptr, do_relu = a.relu != 0;
     int tc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
@@ -410,26 +416,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
       const int m0 = (t % p.n_tiles_n) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * 2 * p.BN);
+      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * p.BN);
       for (int j0 = 0; j0 < p.BN; j0 += 32) {
         const int width = min(32, p.BN - j0);   // 32, or 16 for the last group when BN % 32 == 16
-        for (int h = 0; h < width; h += 16) {
+        const int h = half * 16;
+        if (h < width) {
           uint32_t acc[16], cor[16];
           tmem_ld16(t_main + (uint32_t)(j0 + h), acc);
           tmem_ld16(t_main + (uint32_t)(p.BN + j0 + h), cor);
           tmem_ld_wait();
-          float o[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float4 b4, c4;
+            float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const uint32_t off = 4u * (uint32_t)(m0 + j0 + h + q * 4);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + off));
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            float cc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (has_add) {
+            if (has_add)
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + off));
-              cc[0] = c4.x; cc[1] = c4.y; cc[2] = c4.z; cc[3] = c4.w;
-            }
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+            float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int j = q * 4 + e;
@@ -437,23 +442,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
               val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
               if (has_add) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
               if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
-              o[j] = val;
+              o[e] = val;
             }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
             const int c = (h >> 2) + q;   // 16-byte chunk within the 128-byte slab row
             const uint32_t addr = slab + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[q * 4]), "f"(o[q * 4 + 1]), "f"(o[q * 4 + 2]), "f"(o[q * 4 + 3]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // both halves of the slab are written
         const int c = lane & 7;
         const int m = m0 + j0 + c * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);
-          const int prow = p0 + warp * 32 + rr;
+        for (int i = 0; i < 4; ++i) {
+          const int rr = half * 16 + i * 4 + (lane >> 3);
+          const int prow = p0 + quarter * 32 + rr;
           if (c * 4 < width && prow < p.P && m < a.M && !(p.debug & 4)) {
             float4 val;
             const uint32_t addr = slab + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) << 4);
@@ -469,7 +471,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
             }
           }
         }
-        __syncwarp();   // the slab is rewritten by the next channel group
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // the slab is rewritten by the next channel group
       }
       // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
       tc_fence_before();
@@ -480,7 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
