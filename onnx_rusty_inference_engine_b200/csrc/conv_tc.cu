@@ -365,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = instr_desc_tf32(p.BN);
+      const uint32_t idesc = instr_desc_tf32(p.BN), idesc2 = instr_desc_tf32(2 * p.BN);
       int s = 0;
       uint32_t ph = 0;
       int tc = 0;
@@ -385,11 +385,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
             const uint64_t ah = smem_desc_sw128(a_hi(s) + kk * 32);
             const uint64_t al = smem_desc_sw128(a_lo(s) + kk * 32);
             const uint64_t bh = smem_desc_sw128(b_hi(s) + kk * 32);
-            const uint64_t bl = smem_desc_sw128(b_lo(s) + kk * 32);
             const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-            umma_tf32(d_corr, al, bh, idesc, acc);
-            umma_tf32(d_corr, ah, bl, idesc, 1u);
-            umma_tf32(d_main, ah, bh, idesc, acc);
+            // B_hi and B_lo are adjacent in the stage ([2*BN rows] x 128 B), and so are the two accumulators
+            // ([main | correction] = 2*BN TMEM columns): ONE N = 2*BN instruction computes A_hi*B_hi -> main and
+            // A_hi*B_lo -> correction, reading A_hi once; a second N = BN instruction adds A_lo*B_hi.
+            umma_tf32(d_main, ah, bh, idesc2, acc);
+            umma_tf32(d_corr, al, bh, idesc, 1u);
           }
           umma_commit(empty(s));   // frees the smem stage once the MMAs above have read it
           if (++s == p.S) { s = 0; ph ^= 1u; }
