@@ -245,9 +245,17 @@ def run_own(args):
         bw = [p for p in prof if not p["kind"].startswith("conv") and not p["kind"].startswith("matmul")]
         bw_ms = sum(p["ms"] for p in bw)
         bw_gbs = sum(p["bytes"] for p in bw) / (bw_ms * 1e-3) / 1e9 if bw_ms > 0 else None
+        # DRAM bytes of the same 26 launches from the committed ncu pass (profiles/README.md); null if absent
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r1_tc_step_dram_traffic.json")
+        if os.path.exists(tp) and B == 256 and not args.conv_path:
+            with open(tp) as f:
+                traffic = json.load(f).get("conv_tc_dram_bytes_per_step")
+            traffic_src = "profiles/r1_tc_step_dram_traffic.json (ncu dram__bytes_read+write.sum, 26 conv launches of one step)"
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": achieved / tensor_peak, "traffic": None,
+            "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": "step: the 26 conv launches (one kernel, conv_tc_kernel)",
             "kernel": "conv (all 26 Conv launches of one step: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
             "peak_source": f"{peaks['src']}: bf16_tflops_sustained {peaks['bf16_tflops_sustained']} / 2 (TF32) / 3 (3xTF32)",
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / total_ms if total_ms else None,

@@ -69,19 +69,27 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvArgs a) {
         ra[i] = v;
       }
     } else {
+      // decode (r, s, c) once for the first of the 4 consecutive k and step it (two divisions per k-block per thread)
+      int rr[4], ss[4], cc[4];
+      {
+        const int tap = kk / a.C;
+        int c = kk - tap * a.C, r = tap / a.KW, s = tap - r * a.KW;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rr[j] = r; ss[j] = s; cc[j] = c;
+          if (++c == a.C) { c = 0; if (++s == a.KW) { s = 0; ++r; } }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = kk + j;
           v[j] = 0.f;
-          if (a_valid[i] && k < a.K) {
-            const int tap = k / a.C;
-            const int c = k - tap * a.C;
-            const int r = tap / a.KW, s = tap - r * a.KW;
-            const int h = a_h0[i] + r, w = a_w0[i] + s;
-            if (h >= 0 && h < a.H && w >= 0 && w < a.W) v[j] = __ldg(a_base[i] + ((long long)h * a.W + w) * a.ldx + c);
+          if (a_valid[i] && kk + j < a.K) {
+            const int h = a_h0[i] + rr[j], w = a_w0[i] + ss[j];
+            if ((unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W)
+              v[j] = __ldg(a_base[i] + ((long long)h * a.W + w) * a.ldx + cc[j]);
           }
         }
         ra[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -101,13 +109,12 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(ConvArgs a) {
             if (k < a.K) v = __ldg(reinterpret_cast<const float4*>(wrow + k));
           } else {
             float t[4];
+            int tap = k / a.C, c = k - tap * a.C;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               t[q] = 0.f;
-              if (k + q < a.K) {
-                const int tap = (k + q) / a.C;
-                t[q] = __ldg(wrow + tap * a.wc + (k + q - tap * a.C));  // weight taps are pitched by wc >= C
-              }
+              if (k + q < a.K) t[q] = __ldg(wrow + tap * a.wc + c);  // weight taps are pitched by wc >= C
+              if (++c == a.C) { c = 0; ++tap; }
             }
             v = make_float4(t[0], t[1], t[2], t[3]);
           }
