@@ -46,12 +46,12 @@ constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMA_WARP = 8;
 constexpr int MMA_WARP = 9;
-constexpr int NUM_PROD_WARPS = 16;
+constexpr int NUM_PROD_WARPS = 8;
 constexpr int FENCE_WARP = 10;
 constexpr int PROD_WARP0 = 11;
 constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 864
 constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 2 rows per producer thread per k-block
-constexpr int PREFETCH = 4;                // k-blocks of A loads in flight per producer thread
+constexpr int PREFETCH = 3;                // k-blocks of A loads in flight per producer thread
 constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp pair: 32 rows x 32 channels
 constexpr int EPI_STAGING_BYTES = 4 * EPI_SLAB_BYTES;  // one slab per warp pair: 16 KB
 constexpr int SMEM_MAX = 227 * 1024;
@@ -218,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   if (warp >= PROD_WARP0) {
     // ================================================================ A producers (16 warps)
     // Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, a base pointer (tap (0,0), channel 0) and two
-    // separable validity masks (bit 16*i+r: input row h0+r inside the image; bit 16*i+s: column w0+s inside).
+    // separable validity masks (bit 8*i+r: input row h0+r inside the image; bit 8*i+s: column w0+s inside).
     // Per k-block the chunk's (r, s, c) is decoded once (multiply-high division) into one element offset shared by
     // all rows, so a load costs an add, a mask test and the LDG.
     const int pw = warp - PROD_WARP0;
@@ -256,8 +256,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
         const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
         const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
-        hmask |= hm << (16 * i);
-        wmask |= wm << (16 * i);
+        hmask |= hm << (8 * i);
+        wmask |= wm << (8 * i);
       }
     };
     float4 v[PREFETCH][ROWS_PER_THREAD];
@@ -268,11 +268,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
       const int r = p.magicKW ? (int)__umulhi((unsigned)tap, p.magicKW) : tap;  // tap / KW
       const int sx = tap - r * a.KW;
       const int delta = (r * a.W + sx) * a.ldx + c;
-      const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 16*i: row i valid for this tap
+      const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 8*i: row i valid for this tap
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
         dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (((m >> (16 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
+        if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
       }
       if (++l_kb == p.nkb) {
         l_kb = 0;
@@ -533,7 +533,7 @@ int tc_supported(const ConvArgs& a) {
   if (a.C % 4 != 0 || a.ldx % 4 != 0 || a.wc != a.C) return B200_EUNSUPPORTED;
   if ((((uintptr_t)a.x) & 15) != 0) return B200_EUNSUPPORTED;
   if (a.M < 1 || a.K < 8) return B200_EUNSUPPORTED;
-  if (a.KH > 15 || a.KW > 15 || a.pt > 15 || a.pl > 15 || ROWS_PER_THREAD > 2) return B200_EUNSUPPORTED;                  // 16-bit validity masks per row
+  if (a.KH > 8 || a.KW > 8 || a.pt > 15 || a.pl > 15 || ROWS_PER_THREAD > 4) return B200_EUNSUPPORTED;                  // 16-bit validity masks per row
   if (a.Ho + BM >= 65536 || a.Wo + BM >= 65536) return B200_EUNSUPPORTED;                       // multiply-high division range
   if (a.K >= 65536 || a.C >= 65536) return B200_EUNSUPPORTED;                                 // multiply-high division range
   if ((long long)(a.KH + 1) * a.W * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;           // 32-bit tap offsets
