@@ -26,6 +26,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "internal.h"
 
@@ -48,14 +49,16 @@ constexpr int TMA_WARP = 8;
 constexpr int MMA_WARP = 9;
 constexpr int NUM_PROD_WARPS = 8;
 constexpr int FENCE_WARP = 10;
-constexpr int PROD_WARP0 = 11;
-constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 864
+constexpr int ATMA_WARP = 11;   // pointwise layers: issues the TMA loads of the raw A tiles
+constexpr int PROD_WARP0 = 12;
+constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 640
 constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 2 rows per producer thread per k-block
 constexpr int PREFETCH = 3;                // k-blocks of A loads in flight per producer thread
 constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp pair: 32 rows x 32 channels
 constexpr int EPI_STAGING_BYTES = 4 * EPI_SLAB_BYTES;  // one slab per warp pair: 16 KB
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 6;
+constexpr int MAX_RAW = 8;                 // raw A ring (pointwise / TMA-fed mode)
 
 struct TcParams {
   ConvArgs a;
@@ -68,7 +71,9 @@ struct TcParams {
   int Mpad;        // weight rows per half (hi / lo)
   int P;           // output pixels (fits in int32, checked on the host)
   int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
-  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores
+  int a_tma;       // 1: A tiles arrive by TMA into a raw ring (pointwise layers); 0: register gather
+  int R;           // raw ring slots (a_tma)
+  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 8 skip proxy fence, 16 skip MMAs
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -168,13 +173,14 @@ __device__ __forceinline__ float split_lo(float x, float hi) { return __uint_as_
 
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const ConvArgs& a = p.a;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.BN * BK * 4;
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
-  const uint32_t epi_staging = smem_base + (uint32_t)p.S * stage_bytes;          // 2 KB-aligned slabs
+  const uint32_t raw_ring = smem_base + (uint32_t)p.S * stage_bytes;             // R x 16 KB raw fp32 A tiles (a_tma)
+  const uint32_t epi_staging = raw_ring + (uint32_t)p.R * A_TILE_BYTES;          // 2 KB-aligned slabs
   const uint32_t sbias = epi_staging + EPI_STAGING_BYTES;                        // Mpad floats: bias, zero padded
   const uint32_t sadd = sbias + 4u * (uint32_t)p.Mpad;                           // Mpad floats: folded channel add
   const uint32_t bars = sadd + 4u * (uint32_t)p.Mpad;                            // 8-byte mbarriers
@@ -185,6 +191,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
   auto tmem_full = [&](int s) { return bars + 8u * (4 * MAX_STAGES + s); };
   auto tmem_empty = [&](int s) { return bars + 8u * (4 * MAX_STAGES + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (4 * MAX_STAGES + 4);
+  auto raw_full = [&](int r) { return bars + 8u * (4 * MAX_STAGES + 5 + r); };
+  auto raw_empty = [&](int r) { return bars + 8u * (4 * MAX_STAGES + 5 + MAX_RAW + r); };
   auto a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
   auto a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
   auto b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES; };
@@ -204,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
     if (lane == 0) {
       for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); mbar_init(ready_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
+      for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), NUM_PROD_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -227,6 +236,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
     int my_tiles = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) ++my_tiles;
     const int items = my_tiles * p.nkb;
+
+    if (p.a_tma) {
+      // ---- TMA-fed mode (pointwise layers): the raw fp32 tile of each k-block is already in shared memory, in the
+      // same 128B-swizzled layout as the hi / lo tiles, so a thread converts in place: same offsets in, same out.
+      // Up to R raw tiles (R x 16 KB) are in flight from HBM without costing a register.
+      uint32_t off[ROWS_PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
+        off[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+      }
+      int s = 0, r = 0;
+      uint32_t ph = 0, rph = 0;
+      for (int idx = 0; idx < items; ++idx) {
+        mbar_wait(raw_full(r), rph);
+        const uint32_t raw = raw_ring + (uint32_t)r * A_TILE_BYTES;
+        float4 x[ROWS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
+        float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          hi[i].x = split_hi(x[i].x); hi[i].y = split_hi(x[i].y); hi[i].z = split_hi(x[i].z); hi[i].w = split_hi(x[i].w);
+          lo[i].x = split_lo(x[i].x, hi[i].x); lo[i].y = split_lo(x[i].y, hi[i].y);
+          lo[i].z = split_lo(x[i].z, hi[i].z); lo[i].w = split_lo(x[i].w, hi[i].w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_empty(r));   // the raw slot has been read (values are in registers)
+        if (++r == p.R) { r = 0; rph ^= 1u; }
+        mbar_wait(empty(s), ph ^ 1u);
+        const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off[i]), "f"(hi[i].x), "f"(hi[i].y), "f"(hi[i].z), "f"(hi[i].w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off[i]), "f"(lo[i].x), "f"(lo[i].y), "f"(lo[i].z), "f"(lo[i].w) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(s));
+        if (++s == p.S) { s = 0; ph ^= 1u; }
+      }
+    } else {
 
     int l_tile = blockIdx.x, l_kb = 0;   // load cursor
     const float* base[ROWS_PER_THREAD];
@@ -326,6 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         }
       }
     }
+    }  // register-gather path
   } else if (warp == TMA_WARP) {
     // ================================================================ weight tiles via TMA
     if (lane == 0) {
@@ -343,6 +395,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
         }
       }
     }
+  } else if (warp == ATMA_WARP) {
+    // ================================================================ raw A tiles via TMA (pointwise layers only)
+    if (p.a_tma && lane == 0) {
+      int r = 0;
+      uint32_t rph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int p0 = (t / p.n_tiles_n) * BM;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(raw_empty(r), rph ^ 1u);
+          mbar_expect_tx(raw_full(r), (uint32_t)A_TILE_BYTES);
+          // box = 32 channels x 128 pixel rows; rows past P and channels past C are zero-filled by the tensor map
+          tma_load_2d(raw_ring + (uint32_t)r * A_TILE_BYTES, &tmapA, raw_full(r), kb * BK, p0);
+          if (++r == p.R) { r = 0; rph ^= 1u; }
+        }
+      }
+    }
   } else if (warp == FENCE_WARP) {
     // ================================================================ proxy-fence relay
     // The A tiles are written with ordinary st.shared (generic proxy) and read by tcgen05.mma (async proxy), so a
@@ -356,7 +424,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(full_a(s), ph);
-          fence_proxy_async();
+          if (!(p.debug & 8)) fence_proxy_async();
           mbar_arrive(ready_a(s));
           if (++s == p.S) { s = 0; ph ^= 1u; }
         }
@@ -381,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const TcParams p) {
           mbar_wait(full_b(s), ph);
           tc_fence_after();
           const int ksteps = min(4, (a.K - kb * BK + 7) >> 3);
-          for (int kk = 0; kk < ksteps; ++kk) {
+          for (int kk = 0; kk < ((p.debug & 16) ? 0 : ksteps); ++kk) {
             const uint64_t ah = smem_desc_sw128(a_hi(s) + kk * 32);
             const uint64_t al = smem_desc_sw128(a_lo(s) + kk * 32);
             const uint64_t bh = smem_desc_sw128(b_hi(s) + kk * 32);
@@ -584,12 +652,25 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 4 * p.BN) p.tmem_cols <<= 1;   // 2 stages x (main + correction)
   const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * BK * 4;
-  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (4 * MAX_STAGES + 5);
+  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (4 * MAX_STAGES + 5 + 2 * MAX_RAW);
+  // Pointwise layers (1x1, stride 1, no padding): im2col row p IS input pixel p, so the A operand is a plain 2-D
+  // matrix [P][C] and TMA can stream it; these layers are HBM-bound and want many bytes in flight.
+  static const int no_atma = [] { const char* e = getenv("B200_TC_NO_ATMA"); return e ? atoi(e) : 0; }();
+  p.a_tma = (!no_atma && a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.pt == 0 && a.pl == 0 && a.H == a.Ho && a.W == a.Wo) ? 1 : 0;
+  p.R = 0;
   int S = (SMEM_MAX - fixed) / stage_bytes;
   if (S > MAX_STAGES) S = MAX_STAGES;
+  if (p.a_tma) {
+    if (S > 3) S = 3;
+    if (S > 2 && stage_bytes >= 64 * 1024) S = 2;
+    int R = (SMEM_MAX - fixed - S * stage_bytes) / A_TILE_BYTES;
+    if (R > MAX_RAW) R = MAX_RAW;
+    if (S < 2 || R < 2) { p.a_tma = 0; S = (SMEM_MAX - fixed) / stage_bytes; if (S > MAX_STAGES) S = MAX_STAGES; }
+    else p.R = R;
+  }
   if (S < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 stages (BN=%d)", p.BN);
   p.S = S;
-  const size_t smem = (size_t)S * stage_bytes + fixed;
+  const size_t smem = (size_t)S * stage_bytes + (size_t)p.R * A_TILE_BYTES + fixed;
 
   p.vec_store = (a.ldy % 4 == 0 && (((uintptr_t)a.y) & 15) == 0) ? 1 : 0;
   { static const int dbg = [] { const char* e = getenv("B200_TC_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
@@ -609,7 +690,20 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   }
   const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(w.tmap, p);
+  CUtensorMap tmapA;
+  memset(&tmapA, 0, sizeof(tmapA));
+  if (p.a_tma) {
+    EncodeTiledFn enc = get_encode_fn();
+    cuuint64_t gdim[2] = {(cuuint64_t)a.C, (cuuint64_t)P};
+    cuuint64_t gstride[1] = {(cuuint64_t)a.ldx * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc ? enc(&tmapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                     : CUDA_ERROR_NOT_SUPPORTED;
+    if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
+  }
+  conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
