@@ -1,0 +1,86 @@
+"""Parity of the tcgen05 3xTF32 convolution (csrc/conv_tc.cu) against the CPU oracle and the CUDA-core kernel, over the
+shapes that exercise its code paths: TMA-fed pointwise mode vs register-gather mode, taps changing inside a k-block
+(C = 4, 16, 48), ragged pixel tiles, channel tiles (M > 128), K tails, channel-view inputs and outputs (Concat slices),
+pipeline wrap-around (many k-blocks, many tiles per CTA)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_conv(x, w, b, pads, strides, relu):
+    from oracle import ref_ops as R
+    ap = R.PAD_NOTSET if any(pads) else R.PAD_VALID
+    y = np.stack([R.conv2d_image(x[i], w, b, ap, pads, strides) for i in range(x.shape[0])])
+    return np.maximum(y, 0) if relu else y
+
+
+CASES = [
+    # N, C, H, W, M, k, stride, pad          what it exercises
+    (2, 96, 20, 20, 16, 1, 1, 0),          # pointwise (TMA-fed), 3 k-blocks, 7 pixel tiles, ragged last tile
+    (1, 16, 31, 31, 64, 1, 1, 0),          # pointwise, K = 16 < one k-block (TMA zero-fills channels 16..31)
+    (1, 48, 9, 9, 192, 1, 1, 0),           # pointwise, K = 48 (tail k-block), two channel tiles of 96
+    (1, 512, 13, 13, 1000, 1, 1, 0),       # conv10: 16 k-blocks, 8 channel tiles, M tail (1000 = 7*128 + 104)
+    (2, 4, 57, 57, 96, 7, 2, 0),           # conv1 geometry: C = 4 (a tap per 16-byte chunk), stride 2, K = 196
+    (2, 16, 27, 27, 64, 3, 1, 1),          # expand3x3: C = 16 (two taps per k-block), padding
+    (1, 48, 27, 27, 192, 3, 1, 1),         # C = 48: taps straddle k-block boundaries; 14 k-blocks
+    (3, 64, 13, 13, 256, 3, 1, 1),         # fire8-like: two channel tiles of 128, 18 k-blocks
+    (1, 32, 40, 40, 128, 3, 2, 1),         # strided 3x3 with padding
+    (40, 32, 54, 54, 128, 1, 1, 0),        # 912 tiles > 148 CTAs: several tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"tc{i}" for i in range(len(CASES))])
+def test_conv_tc_vs_oracle(ctx, case):
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    N, C, H, W, M, k, s, p = case
+    rng = np.random.default_rng(hash(case) % (2**32))
+    x = (rng.standard_normal((N, C, H, W)) * 3).astype(np.float32)
+    w = (rng.uniform(-1, 1, (M, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, (M,)).astype(np.float32)
+    n_chk = min(N, 2)                       # the oracle is slow: check the first and the last image
+    idx = [0, N - 1][:n_chk]
+    want = _oracle_conv(x[idx], w, b, (p,) * 4, (s, s), relu=True)
+    y = L.conv2d(ctx, ctx.tensor(x), ctx.tensor(w), bias=ctx.tensor(b), strides=(s, s), pads=(p,) * 4, fuse_relu=True)
+    got = y.numpy()
+    assert_close(got[idx], want, f"conv_tc {case}")
+    if N > 2:   # images in the middle: batch-position invariance against the checked ones is covered by x being iid;
+        assert np.isfinite(got).all()
+
+
+def test_conv_tc_channel_views(ctx):
+    """Input is a channel slice of a wider tensor (pitch > C: what a Conv reading half of a Concat result sees) and the
+    output is a channel slice too; both the TMA-fed (1x1) and the gather (3x3) modes."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(11)
+    big = (rng.standard_normal((2, 96, 14, 14)) * 2).astype(np.float32)
+    tbig = ctx.tensor(big)
+    xin = tbig.view_channels(32, 32)                      # channels 32..63, pitch 96
+    x = big[:, 32:64]
+    for k, p in ((1, 0), (3, 1)):
+        w = (rng.uniform(-1, 1, (48, 32, k, k)) / np.sqrt(32 * k * k)).astype(np.float32)
+        b = rng.uniform(-0.5, 0.5, (48,)).astype(np.float32)
+        want = _oracle_conv(x, w, b, (p,) * 4, (1, 1), relu=False)
+        out = L.DeviceTensor.alloc(ctx, (2, 112, 14, 14))
+        out.upload(np.full((2, 112, 14, 14), 7.0, np.float32))
+        L.conv2d(ctx, xin, ctx.tensor(w), bias=ctx.tensor(b), strides=(1, 1), pads=(p,) * 4, y=out.view_channels(16, 48))
+        got = out.numpy()
+        assert_close(got[:, 16:64], want, f"view conv k={k}")
+        assert (got[:, :16] == 7.0).all() and (got[:, 64:] == 7.0).all(), "wrote outside the channel slice"
+
+
+def test_conv_tc_matches_cuda_core_path_in_fresh_process():
+    """Same convolutions through the CUDA-core fp32 kernel (B200_CONV_PATH=1) and through tcgen05 in two fresh
+    processes: both within tolerance of an fp64 reference (tools/tc_check.py), i.e. of each other."""
+    env = dict(os.environ)
+    for path in ("0", "1"):
+        env["B200_CONV_PATH"] = path
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tc_check.py")], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, f"conv path {path}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
