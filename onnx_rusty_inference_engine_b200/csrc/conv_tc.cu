@@ -73,7 +73,7 @@ struct TcParams {
   int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
   int a_tma;       // 1: A tiles arrive by TMA into a raw ring (pointwise layers); 0: register gather
   int R;           // raw ring slots (a_tma)
-  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 8 skip proxy fence, 16 skip MMAs
+  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 8 skip proxy fence, 16 skip MMAs, 32 skip the gather producers' st.shared
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -149,6 +149,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [32,46) stride byte offset >> 4 (1024 B between 8-row groups)   [46,48) version = 1   [61,64) layout = 2 (SW128)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// the same descriptor from a precomputed low word (address >> 4 | LBO); the high word is constant
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t lo) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(0x40004040u));   // SBO 1024 >> 4, version 1, SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 // cute::UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b format TF32 [7,10)=[10,13)=2, K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t instr_desc_tf32(int n) {
@@ -363,6 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            if (p.debug & 32) break;
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + soff[i]), "f"(hi[i].x), "f"(hi[i].y), "f"(hi[i].z), "f"(hi[i].w) : "memory");
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + soff[i]), "f"(lo[i].x), "f"(lo[i].y), "f"(lo[i].z), "f"(lo[i].w) : "memory");
           }
@@ -432,40 +450,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     }
   } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc_tf32(p.BN), idesc2 = instr_desc_tf32(2 * p.BN);
-      int s = 0;
-      uint32_t ph = 0;
-      int tc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
-        const int as = tc & 1;
-        const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
-        mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
+    // The whole warp walks the pipeline (uniform control flow, barrier waits by all lanes); one elected lane issues.
+    // The issue stream is the kernel's critical resource (measured: the time per k-block did not depend on BN while
+    // descriptors were rebuilt from addresses inside a single-lane branch), so the 64-bit shared-memory descriptors
+    // are kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
+    const uint32_t idesc = instr_desc_tf32(p.BN), idesc2 = instr_desc_tf32(2 * p.BN);
+    const bool leader = elect_one();
+    const uint32_t lo_first = ((a_hi(0) >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
+    const uint32_t lo_step = (uint32_t)stage_bytes >> 4;
+    const uint32_t lo_wrap = lo_first + (uint32_t)p.S * lo_step;
+    uint32_t lo = lo_first;
+    int s = 0;
+    uint32_t ph = 0;
+    int tc = 0;
+    const int tail_ksteps = ((a.K - (p.nkb - 1) * BK + 7) >> 3);   // k-steps of the last k-block (1..4)
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
+      const int as = tc & 1;
+      const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
+      mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
+      const uint32_t d_corr = d_main + (uint32_t)p.BN;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(ready_a(s), ph);  // A stage written, released, and proxy-fenced by the fence warp
+        mbar_wait(full_b(s), ph);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
-        const uint32_t d_corr = d_main + (uint32_t)p.BN;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(ready_a(s), ph);  // A stage written, released, and proxy-fenced by the fence warp
-          mbar_wait(full_b(s), ph);
-          tc_fence_after();
-          const int ksteps = min(4, (a.K - kb * BK + 7) >> 3);
-          for (int kk = 0; kk < ((p.debug & 16) ? 0 : ksteps); ++kk) {
-            const uint64_t ah = smem_desc_sw128(a_hi(s) + kk * 32);
-            const uint64_t al = smem_desc_sw128(a_lo(s) + kk * 32);
-            const uint64_t bh = smem_desc_sw128(b_hi(s) + kk * 32);
-            const uint32_t acc = (kb | kk) != 0 ? 1u : 0u;
-            // B_hi and B_lo are adjacent in the stage ([2*BN rows] x 128 B), and so are the two accumulators
-            // ([main | correction] = 2*BN TMEM columns): ONE N = 2*BN instruction computes A_hi*B_hi -> main and
-            // A_hi*B_lo -> correction, reading A_hi once; a second N = BN instruction adds A_lo*B_hi.
-            umma_tf32(d_main, ah, bh, idesc2, acc);
-            umma_tf32(d_corr, al, bh, idesc, 1u);
+        if (leader && !(p.debug & 16)) {
+          const uint32_t ah = lo, al = lo + (A_TILE_BYTES >> 4), bh = lo + 2 * (A_TILE_BYTES >> 4);
+          const int ksteps = (kb == p.nkb - 1) ? tail_ksteps : 4;
+          // B_hi and B_lo are adjacent in the stage ([2*BN rows] x 128 B), and so are the two accumulators
+          // ([main | correction] = 2*BN TMEM columns): ONE N = 2*BN instruction computes A_hi*B_hi -> main and
+          // A_hi*B_lo -> correction, reading A_hi once; a second N = BN instruction adds A_lo*B_hi.
+          umma_tf32(d_main, sw128_desc(ah), sw128_desc(bh), idesc2, kb != 0 ? 1u : 0u);
+          umma_tf32(d_corr, sw128_desc(al), sw128_desc(bh), idesc, 1u);
+#pragma unroll
+          for (int kk = 1; kk < 4; ++kk) {
+            if (kk < ksteps) {
+              umma_tf32(d_main, sw128_desc(ah + 2 * kk), sw128_desc(bh + 2 * kk), idesc2, 1u);
+              umma_tf32(d_corr, sw128_desc(al + 2 * kk), sw128_desc(bh + 2 * kk), idesc, 1u);
+            }
           }
-          umma_commit(empty(s));   // frees the smem stage once the MMAs above have read it
-          if (++s == p.S) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
+        __syncwarp();
+        if (leader) umma_commit(empty(s));   // frees the smem stage once the MMAs above have read it
+        lo += lo_step;
+        if (++s == p.S) { s = 0; ph ^= 1u; lo = lo_first; }
       }
+      if (leader) umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
+      __syncwarp();
     }
+    (void)lo_wrap;
   } else {
     // ================================================================ epilogue (warps 0-7)
     // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w and w+4 form a pair on the same 32 accumulator
@@ -590,6 +624,8 @@ EncodeTiledFn get_encode_fn() {
 
 // BN: the smallest multiple of 16 that covers M in ceil(M / 128) channel tiles.
 int pick_bn(int M) {
+  static const int force = [] { const char* e = getenv("B200_TC_BN"); return e ? atoi(e) : 0; }();   // experiments only
+  if (force >= 16 && force <= 128 && force % 16 == 0 && M > force) return force;
   const int nt = (M + 127) / 128;
   const int per = (M + nt - 1) / nt;
   return (per + 15) & ~15;
