@@ -1,4 +1,4 @@
-// tcgen05 3xTF32 implicit-GEMM convolution for sm_100a -- persistent, warp-specialised.
+// tcgen05 3xTF32 implicit-GEMM convolution for sm_100a -- persistent, warp-specialised, A operand in tensor memory.
 //
 // Semantics: conv2d, convolution_op.rs:224-517 (+ folded Add add_op.rs:75 and Relu relu_op.rs:31-33), identical to
 // conv_simt.cu.  fp32 accuracy is kept by splitting every operand x into hi = rna_tf32(x) and lo = rna_tf32(x - hi)
@@ -8,21 +8,30 @@
 // sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.
 //
 // GEMM view: D[P x M] = A[P x K] * W[M x K]^T, P = N*Ho*Wo output pixels, K = KH*KW*C ordered (r, s, c).
-//   UMMA tile 128 pixels (TMEM lanes) x BN <= 128 output channels (TMEM columns), k-block = 32 floats = one 128-byte
-//   swizzle row = 4 k-steps of 8, kind::tf32, cta_group::1, both operands K-major in shared memory.
-//   TMEM: 2 accumulator stages x {main, correction} x BN columns (<= 512), so the epilogue of tile i overlaps the
-//   main loop of tile i+1.
-// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 27 warps:
-//   warps 0-7   epilogue (pairs w, w+4 share TMEM lanes 32*(w%4).. and split the channels): tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..), + bias (+ channel add), Relu,
-//               transpose 32 rows x 32 channels through swizzled shared memory and write complete 128-byte row
-//               segments at the (channel-offset) destination.
-//   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the pre-split weight tiles.
-//   warp 9      one thread issues tcgen05.mma / tcgen05.commit.
-//   warp 10     proxy-fence relay (see below)
-//   warps 11-26 A producers: gather im2col rows straight from the channels-last activation (any stride / padding /
-//               tap; 16-byte chunks; 4 k-blocks of loads in flight per thread), split hi/lo in registers, store both
-//               tiles in the 128B-swizzled K-major layout UMMA expects, fence.proxy.async, arrive.
-// Weights are split, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
+//   UMMA tile 128 pixels (TMEM lanes) x BN <= 128 output channels (TMEM columns), k-block = 32 floats = 4 k-steps of
+//   8, kind::tf32, cta_group::1.
+//   A (activations): gathered to REGISTERS, split there, and written straight into TENSOR MEMORY with tcgen05.st
+//     (16x256b: a thread owns 16-byte chunks of rows t/4 + 8i) -- the MMAs take A from TMEM, so the activations never
+//     touch shared memory: no st.shared, no A operand reads on the shared-memory port, no generic->async proxy fence.
+//   B (weights): pre-split (hi, lo) K-major tiles streamed by TMA into a SWIZZLE_128B ring.  The 16x256b store shape
+//     puts float 4c+e of a 16-float group in TMEM column 2c+e (e < 2) or 8+2c+e-2 (e >= 2), so the weight
+//     preparation applies the same permutation to K inside every group of 16 (a contraction does not care).
+//   TMEM columns (512): [accumulator stages: {main | correction} x BN each][A stages: {hi 32 | lo 32} each].
+//     BN <= 96: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1);
+//     BN  > 96: one accumulator stage, four A stages; the epilogue drains TMEM to a shared-memory slab first and
+//     releases the accumulator before it touches global memory.
+// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 20 warps:
+//   warps 0-7   epilogue: warps w, w+4 share TMEM lanes 32*(w%4).. and take the two halves of the tile's channels.
+//               Phase 1 drains: tcgen05.ld main + correction, add, + bias (+ channel add), Relu, row-per-thread into a
+//               private swizzled slab; then the accumulator stage is handed back.  Phase 2 writes the slab out with
+//               16-byte chunks, consecutive lanes along a row (complete 32-byte sectors of the channels-last rows).
+//   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the weight tiles.
+//   warp 9      MMA issuer (uniform control flow, one elected lane, descriptors advanced by adds).
+//   warp 10     pointwise layers: TMA loads of raw fp32 A tiles into a shared-memory ring.
+//   warps 12-19 A producers: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and the 64-byte half (w-12)/4 of each
+//               k-block row.  Gather mode: im2col rows straight from the channels-last activation (any stride /
+//               padding / tap; 3 k-blocks of loads in flight per thread).  Pointwise mode: read the TMA-fed raw tile.
+// Weights are split, permuted, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -43,37 +52,38 @@ namespace {
 
 constexpr int BM = 128;                    // pixels per tile (UMMA M)
 constexpr int BK = 32;                     // floats per k-block (128 bytes)
-constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB (raw fp32 A tile of the pointwise mode)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMA_WARP = 8;
 constexpr int MMA_WARP = 9;
+constexpr int ATMA_WARP = 10;   // pointwise layers: issues the TMA loads of the raw A tiles
 constexpr int NUM_PROD_WARPS = 8;
-constexpr int FENCE_WARP = 10;
-constexpr int ATMA_WARP = 11;   // pointwise layers: issues the TMA loads of the raw A tiles
-constexpr int PROD_WARP0 = 12;
+constexpr int PROD_WARP0 = 12;  // a multiple of 4: producer warp w writes TMEM lanes 32*(w%4)..
 constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 640
-constexpr int ROWS_PER_THREAD = BM / (NUM_PROD_WARPS * 4);   // 2 rows per producer thread per k-block
+constexpr int ROWS_PER_THREAD = 4;         // rows lane/4 + 8i of the warp's 32-row quarter
 constexpr int PREFETCH = 3;                // k-blocks of A loads in flight per producer thread
-constexpr int EPI_SLAB_BYTES = 32 * 32 * 4;  // per epilogue warp pair: 32 rows x 32 channels
-constexpr int EPI_STAGING_BYTES = 4 * EPI_SLAB_BYTES;  // one slab per warp pair: 16 KB
+constexpr int A_STAGE_COLS = 64;           // TMEM columns per A stage: hi 32 | lo 32
+constexpr int MAX_A_STAGES = 4;
 constexpr int SMEM_MAX = 227 * 1024;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 6;              // weight ring
 constexpr int MAX_RAW = 8;                 // raw A ring (pointwise / TMA-fed mode)
 
 struct TcParams {
   ConvArgs a;
   int BN;          // output channels per tile (multiple of 16, <= 128)
-  int S;           // smem pipeline stages
+  int S;           // weight ring stages (shared memory)
+  int SA;          // A stages (tensor memory)
+  int nacc;        // accumulator stages (tensor memory): 2 when 4*BN + 2*64 <= 512, else 1
   int nkb;         // k-blocks per tile
   int n_tiles_n;   // channel tiles
   int total_tiles; // pixel tiles x channel tiles
-  int tmem_cols;   // power of two >= 4*BN
   int Mpad;        // weight rows per half (hi / lo)
   int P;           // output pixels (fits in int32, checked on the host)
   int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
   int a_tma;       // 1: A tiles arrive by TMA into a raw ring (pointwise layers); 0: register gather
   int R;           // raw ring slots (a_tma)
-  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 8 skip proxy fence, 16 skip MMAs, 32 skip the gather producers' st.shared
+  int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
+  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -102,7 +112,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -120,17 +129,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, single CTA.  A: lanes = rows, one 32-bit column per k element.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 16 TMEM lanes x 16 columns from 8 registers per thread: thread t writes rows t/4 (r0 r1 | r4 r5) and t/4 + 8
+// (r2 r3 | r6 r7), columns 2*(t%4) + {0, 1} and 8 + 2*(t%4) + {0, 1}  (layout measured with tools/exp/tmem_layout.cu)
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(r0), "f"(r1),
+               "f"(r2), "f"(r3), "f"(r4), "f"(r5), "f"(r6), "f"(r7)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -147,10 +164,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 (1024 B between 8-row groups)   [46,48) version = 1   [61,64) layout = 2 (SW128)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// the same descriptor from a precomputed low word (address >> 4 | LBO); the high word is constant
+// built from a precomputed low word (address >> 4 | LBO); the high word is constant
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t lo) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(0x40004040u));   // SBO 1024 >> 4, version 1, SWIZZLE_128B
@@ -188,6 +202,27 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ float split_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float split_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) + 0x1000u); }
 
+// A producer's four 16-byte chunks (rows lane/4 + 8i of its 32-row quarter), split into hi / lo
+struct SplitRows { float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD]; };
+__device__ __forceinline__ void split_rows(const float4 (&x)[ROWS_PER_THREAD], SplitRows& o) {
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    o.hi[i].x = split_hi(x[i].x); o.hi[i].y = split_hi(x[i].y); o.hi[i].z = split_hi(x[i].z); o.hi[i].w = split_hi(x[i].w);
+    o.lo[i].x = split_lo(x[i].x, o.hi[i].x); o.lo[i].y = split_lo(x[i].y, o.hi[i].y);
+    o.lo[i].z = split_lo(x[i].z, o.hi[i].z); o.lo[i].w = split_lo(x[i].w, o.hi[i].w);
+  }
+}
+// ... and written to the warp's part of an A stage in tensor memory: hi -> columns [0,32), lo -> [32,64) of the stage;
+// t_stage = lane 32*quarter, column of the warp's 16-column half.  Two 16-lane halves: rows i = 2j, 2j+1.
+__device__ __forceinline__ void store_rows(uint32_t t_stage, const SplitRows& o) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t ta = t_stage + ((uint32_t)(j * 16) << 16);
+    tmem_st_16x256b_x2(ta, o.hi[2 * j].x, o.hi[2 * j].y, o.hi[2 * j + 1].x, o.hi[2 * j + 1].y, o.hi[2 * j].z, o.hi[2 * j].w, o.hi[2 * j + 1].z, o.hi[2 * j + 1].w);
+    tmem_st_16x256b_x2(ta + 32u, o.lo[2 * j].x, o.lo[2 * j].y, o.lo[2 * j + 1].x, o.lo[2 * j + 1].y, o.lo[2 * j].z, o.lo[2 * j].w, o.lo[2 * j + 1].z, o.lo[2 * j + 1].w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
@@ -195,25 +230,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   const ConvArgs& a = p.a;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.BN * BK * 4;
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+  const int stage_bytes = 2 * b_tile_bytes;                                      // B_hi | B_lo
   const uint32_t raw_ring = smem_base + (uint32_t)p.S * stage_bytes;             // R x 16 KB raw fp32 A tiles (a_tma)
-  const uint32_t epi_staging = raw_ring + (uint32_t)p.R * A_TILE_BYTES;          // 2 KB-aligned slabs
-  const uint32_t sbias = epi_staging + EPI_STAGING_BYTES;                        // Mpad floats: bias, zero padded
+  const uint32_t epi_slabs = raw_ring + (uint32_t)p.R * A_TILE_BYTES;            // 8 x 32 rows x slab_pitch
+  const uint32_t sbias = epi_slabs + (uint32_t)(NUM_EPI_WARPS * 32 * p.slab_pitch);  // Mpad floats: bias, zero padded
   const uint32_t sadd = sbias + 4u * (uint32_t)p.Mpad;                           // Mpad floats: folded channel add
   const uint32_t bars = sadd + 4u * (uint32_t)p.Mpad;                            // 8-byte mbarriers
-  auto full_a = [&](int s) { return bars + 8u * s; };
-  auto full_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
-  auto empty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
-  auto ready_a = [&](int s) { return bars + 8u * (3 * MAX_STAGES + s); };
-  auto tmem_full = [&](int s) { return bars + 8u * (4 * MAX_STAGES + s); };
-  auto tmem_empty = [&](int s) { return bars + 8u * (4 * MAX_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bars + 8u * (4 * MAX_STAGES + 4);
-  auto raw_full = [&](int r) { return bars + 8u * (4 * MAX_STAGES + 5 + r); };
-  auto raw_empty = [&](int r) { return bars + 8u * (4 * MAX_STAGES + 5 + MAX_RAW + r); };
-  auto a_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes; };
-  auto a_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + A_TILE_BYTES; };
-  auto b_hi = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES; };
-  auto b_lo = [&](int s) { return smem_base + (uint32_t)s * stage_bytes + 2 * A_TILE_BYTES + b_tile_bytes; };
+  auto full_b = [&](int s) { return bars + 8u * s; };
+  auto empty_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+  auto full_a = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
+  auto empty_a = [&](int s) { return bars + 8u * (2 * MAX_STAGES + MAX_A_STAGES + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 4);
+  auto raw_full = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + r); };
+  auto raw_empty = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + MAX_RAW + r); };
+  const int a_col0 = p.nacc * 2 * p.BN;   // first TMEM column of the A stages
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -227,13 +259,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 
   if (warp == TMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < p.S; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); mbar_init(ready_a(s), 1); }
+      for (int s = 0; s < p.S; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+      for (int s = 0; s < p.SA; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(empty_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
       for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), NUM_PROD_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_alloc(tmem_slot, 512u);   // one CTA per SM: the whole tensor memory
   }
   tc_fence_before();
   __syncthreads();
@@ -242,29 +275,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp >= PROD_WARP0) {
-    // ================================================================ A producers (16 warps)
-    // Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, a base pointer (tap (0,0), channel 0) and two
-    // separable validity masks (bit 8*i+r: input row h0+r inside the image; bit 8*i+s: column w0+s inside).
-    // Per k-block the chunk's (r, s, c) is decoded once (multiply-high division) into one element offset shared by
-    // all rows, so a load costs an add, a mask test and the LDG.
+    // ================================================================ A producers (8 warps)
+    // Warp w may only write TMEM lanes 32*(w % 4) .. +31: it owns rows 32*quarter + 8*i + lane/4 (i = 0..3) of the
+    // tile and the 16-byte chunk 4*khalf + lane%4 of each 128-byte k-block row.
     const int pw = warp - PROD_WARP0;
-    const int chunk = lane & 7;      // 16-byte chunk within the 128-byte k-block row
-    const int rsub = lane >> 3;      // 4 rows per warp-wide access
+    const int quarter = pw & 3, khalf = pw >> 2;
+    const int chunk = khalf * 4 + (lane & 3);
+    const int rsub = lane >> 2;
     int my_tiles = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) ++my_tiles;
     const int items = my_tiles * p.nkb;
+    // TMEM address of this warp's part of A stage 0: lane 32*quarter, column a_col0 + 16*khalf
+    const uint32_t t_a0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a_col0 + khalf * 16);
 
     if (p.a_tma) {
-      // ---- TMA-fed mode (pointwise layers): the raw fp32 tile of each k-block is already in shared memory, in the
-      // same 128B-swizzled layout as the hi / lo tiles, so a thread converts in place: same offsets in, same out.
-      // Up to R raw tiles (R x 16 KB) are in flight from HBM without costing a register.
+      // ---- TMA-fed mode (pointwise layers): the raw fp32 tile of each k-block is in shared memory (128B-swizzled
+      // rows); up to R raw tiles (R x 16 KB) are in flight from HBM without costing a register.
       uint32_t off[ROWS_PER_THREAD];
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
+        const int row = quarter * 32 + i * 8 + rsub;
         off[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
       }
-      int s = 0, r = 0;
+      int sa = 0, r = 0;
       uint32_t ph = 0, rph = 0;
       for (int idx = 0; idx < items; ++idx) {
         mbar_wait(raw_full(r), rph);
@@ -273,129 +306,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i)
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
-        float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          hi[i].x = split_hi(x[i].x); hi[i].y = split_hi(x[i].y); hi[i].z = split_hi(x[i].z); hi[i].w = split_hi(x[i].w);
-          lo[i].x = split_lo(x[i].x, hi[i].x); lo[i].y = split_lo(x[i].y, hi[i].y);
-          lo[i].z = split_lo(x[i].z, hi[i].z); lo[i].w = split_lo(x[i].w, hi[i].w);
-        }
+        SplitRows hl;
+        split_rows(x, hl);
         __syncwarp();
         if (lane == 0) mbar_arrive(raw_empty(r));   // the raw slot has been read (values are in registers)
         if (++r == p.R) { r = 0; rph ^= 1u; }
-        mbar_wait(empty(s), ph ^ 1u);
-        const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off[i]), "f"(hi[i].x), "f"(hi[i].y), "f"(hi[i].z), "f"(hi[i].w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off[i]), "f"(lo[i].x), "f"(lo[i].y), "f"(lo[i].z), "f"(lo[i].w) : "memory");
-        }
+        mbar_wait(empty_a(sa), ph ^ 1u);
+        tc_fence_after();
+        if (!(p.debug & 32)) store_rows(t_a0 + (uint32_t)(sa * A_STAGE_COLS), hl);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_a(s));
-        if (++s == p.S) { s = 0; ph ^= 1u; }
+        if (lane == 0) mbar_arrive(full_a(sa));
+        if (++sa == p.SA) { sa = 0; ph ^= 1u; }
       }
     } else {
+      // ---- register gather.  Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, a base pointer (tap
+      // (0,0), channel 0) and two separable validity masks (bit 8*i+r: input row h0+r inside the image; bit 8*i+s:
+      // column w0+s inside).  Per k-block the chunk's (r, s, c) is decoded once (multiply-high division) into one
+      // element offset shared by all rows, so a load costs an add, a mask test and the LDG.
+      int l_tile = blockIdx.x, l_kb = 0;   // load cursor
+      const float* base[ROWS_PER_THREAD];
+      uint32_t hmask = 0, wmask = 0;
+      auto set_tile = [&](int tile) {
+        // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
+        // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
+        const int p0 = (tile / p.n_tiles_n) * BM;
+        const int t0 = p0 / a.Wo, wo0 = p0 - t0 * a.Wo;
+        const int n0 = t0 / a.Ho, ho0 = t0 - n0 * a.Ho;
+        hmask = 0; wmask = 0;
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const int row = quarter * 32 + i * 8 + rsub;
+          const bool ok = p0 + row < p.P;
+          const int wsum = wo0 + row;
+          const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
+          const int wo = wsum - cw * a.Wo;
+          const int hsum = ho0 + cw;
+          const int ch = p.magicHo ? (int)__umulhi((unsigned)hsum, p.magicHo) : hsum;   // hsum / Ho
+          const int ho = hsum - ch * a.Ho;
+          const int n = n0 + ch;
+          const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
+          base[i] = a.x + ((long long)n * a.H * a.W + (long long)h0 * a.W + w0) * a.ldx;
+          // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
+          const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
+          const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
+          const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
+          const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
+          hmask |= hm << (8 * i);
+          wmask |= wm << (8 * i);
+        }
+      };
+      float4 v[PREFETCH][ROWS_PER_THREAD];
+      auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
+        const int k = l_kb * BK + chunk * 4;
+        const int tap = p.magicC ? (int)__umulhi((unsigned)k, p.magicC) : k;      // k / C
+        const int c = k - tap * a.C;
+        const int r = p.magicKW ? (int)__umulhi((unsigned)tap, p.magicKW) : tap;  // tap / KW
+        const int sx = tap - r * a.KW;
+        const int delta = (r * a.W + sx) * a.ldx + c;
+        const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 8*i: row i valid for this tap
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
+        }
+        if (++l_kb == p.nkb) {
+          l_kb = 0;
+          l_tile += gridDim.x;
+          if (l_tile < p.total_tiles) set_tile(l_tile);
+        }
+      };
+      if (items > 0) set_tile(l_tile);
+#pragma unroll
+      for (int d = 0; d < PREFETCH; ++d)
+        if (d < items) issue(v[d]);
 
-    int l_tile = blockIdx.x, l_kb = 0;   // load cursor
-    const float* base[ROWS_PER_THREAD];
-    uint32_t hmask = 0, wmask = 0;
-    auto set_tile = [&](int tile) {
-      // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
-      // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
-      const int p0 = (tile / p.n_tiles_n) * BM;
-      const int t0 = p0 / a.Wo, wo0 = p0 - t0 * a.Wo;
-      const int n0 = t0 / a.Ho, ho0 = t0 - n0 * a.Ho;
-      hmask = 0; wmask = 0;
+      int sa = 0;
+      uint32_t ph = 0;
+      for (int base_i = 0; base_i < items; base_i += PREFETCH) {
 #pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
-        const bool ok = p0 + row < p.P;
-        const int wsum = wo0 + row;
-        const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
-        const int wo = wsum - cw * a.Wo;
-        const int hsum = ho0 + cw;
-        const int ch = p.magicHo ? (int)__umulhi((unsigned)hsum, p.magicHo) : hsum;   // hsum / Ho
-        const int ho = hsum - ch * a.Ho;
-        const int n = n0 + ch;
-        const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
-        base[i] = a.x + ((long long)n * a.H * a.W + (long long)h0 * a.W + w0) * a.ldx;
-        // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
-        const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
-        const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
-        const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
-        const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
-        hmask |= hm << (8 * i);
-        wmask |= wm << (8 * i);
-      }
-    };
-    float4 v[PREFETCH][ROWS_PER_THREAD];
-    auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
-      const int k = l_kb * BK + chunk * 4;
-      const int tap = p.magicC ? (int)__umulhi((unsigned)k, p.magicC) : k;      // k / C
-      const int c = k - tap * a.C;
-      const int r = p.magicKW ? (int)__umulhi((unsigned)tap, p.magicKW) : tap;  // tap / KW
-      const int sx = tap - r * a.KW;
-      const int delta = (r * a.W + sx) * a.ldx + c;
-      const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 8*i: row i valid for this tap
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
-      }
-      if (++l_kb == p.nkb) {
-        l_kb = 0;
-        l_tile += gridDim.x;
-        if (l_tile < p.total_tiles) set_tile(l_tile);
-      }
-    };
-    if (items > 0) set_tile(l_tile);
-#pragma unroll
-    for (int d = 0; d < PREFETCH; ++d)
-      if (d < items) issue(v[d]);
-
-    // smem offsets of this thread's rows inside a tile (fixed for the whole kernel)
-    uint32_t soff[ROWS_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      const int row = pw * (4 * ROWS_PER_THREAD) + i * 4 + rsub;
-      soff[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-    }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int base_i = 0; base_i < items; base_i += PREFETCH) {
-#pragma unroll
-      for (int d = 0; d < PREFETCH; ++d) {
-        const int idx = base_i + d;
-        if (idx < items) {
-          // split in registers first (independent of the stage), then wait for the stage and store
-          float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
-#pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            const float4 x = v[d][i];
-            hi[i].x = split_hi(x.x); hi[i].y = split_hi(x.y); hi[i].z = split_hi(x.z); hi[i].w = split_hi(x.w);
-            lo[i].x = split_lo(x.x, hi[i].x); lo[i].y = split_lo(x.y, hi[i].y);
-            lo[i].z = split_lo(x.z, hi[i].z); lo[i].w = split_lo(x.w, hi[i].w);
+        for (int d = 0; d < PREFETCH; ++d) {
+          const int idx = base_i + d;
+          if (idx < items) {
+            // split in registers first (independent of the stage), then wait for the stage and store
+            SplitRows hl;
+            split_rows(v[d], hl);
+            mbar_wait(empty_a(sa), ph ^ 1u);   // the MMAs that read this A stage have completed
+            tc_fence_after();
+            if (!(p.debug & 32)) store_rows(t_a0 + (uint32_t)(sa * A_STAGE_COLS), hl);
+            if (idx + PREFETCH < items) issue(v[d]);   // next loads go out before the store wait
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(sa));
+            if (++sa == p.SA) { sa = 0; ph ^= 1u; }
           }
-          mbar_wait(empty(s), ph ^ 1u);
-          const uint32_t hi_base = a_hi(s), lo_base = a_lo(s);
-#pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            if (p.debug & 32) break;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + soff[i]), "f"(hi[i].x), "f"(hi[i].y), "f"(hi[i].z), "f"(hi[i].w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + soff[i]), "f"(lo[i].x), "f"(lo[i].y), "f"(lo[i].z), "f"(lo[i].w) : "memory");
-          }
-          // No proxy fence here: a fence in this thread would also wait for the PREFETCH-1 k-blocks of global
-          // loads it still has in flight and serialise the pipeline.  The stores are released by the mbarrier
-          // arrive below; the MMA thread acquires them with its wait on full_a and issues the generic->async
-          // proxy fence itself, immediately before the tcgen05.mma that reads this stage.
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full_a(s));
-          if (idx + PREFETCH < items) issue(v[d]);
-          if (++s == p.S) { s = 0; ph ^= 1u; }
         }
       }
     }
-    }  // register-gather path
   } else if (warp == TMA_WARP) {
     // ================================================================ weight tiles via TMA
     if (lane == 0) {
@@ -404,11 +413,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int m0 = (t % p.n_tiles_n) * p.BN;
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(empty(s), ph ^ 1u);
+          mbar_wait(empty_b(s), ph ^ 1u);
+          const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
           if (p.debug & 1) { mbar_arrive(full_b(s)); if (++s == p.S) { s = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(full_b(s), 2u * (uint32_t)b_tile_bytes);
-          tma_load_2d(b_hi(s), &tmapB, full_b(s), kb * BK, m0);
-          tma_load_2d(b_lo(s), &tmapB, full_b(s), kb * BK, p.Mpad + m0);
+          tma_load_2d(dst, &tmapB, full_b(s), kb * BK, m0);
+          tma_load_2d(dst + b_tile_bytes, &tmapB, full_b(s), kb * BK, p.Mpad + m0);
           if (++s == p.S) { s = 0; ph ^= 1u; }
         }
       }
@@ -429,157 +439,143 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         }
       }
     }
-  } else if (warp == FENCE_WARP) {
-    // ================================================================ proxy-fence relay
-    // The A tiles are written with ordinary st.shared (generic proxy) and read by tcgen05.mma (async proxy), so a
-    // fence.proxy.async has to sit between them.  It compiles to MEMBAR.ALL.CTA: in a producer thread it would wait
-    // for that thread's prefetched global loads, in the MMA thread it would wait for the MMAs in flight -- either
-    // way one fence per k-block serialises the pipeline (measured: ~1.8K clk per k-block for every layer).  This
-    // thread has nothing outstanding: it acquires full_a, fences, and releases ready_a to the MMA thread.
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(full_a(s), ph);
-          if (!(p.debug & 8)) fence_proxy_async();
-          mbar_arrive(ready_a(s));
-          if (++s == p.S) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
   } else if (warp == MMA_WARP) {
     // ================================================================ MMA issuer
     // The whole warp walks the pipeline (uniform control flow, barrier waits by all lanes); one elected lane issues.
-    // The issue stream is the kernel's critical resource (measured: the time per k-block did not depend on BN while
-    // descriptors were rebuilt from addresses inside a single-lane branch), so the 64-bit shared-memory descriptors
-    // are kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
+    // The issue stream is a critical resource (measured: while descriptors were rebuilt from addresses inside a
+    // single-lane branch the time per k-block did not depend on BN), so the 64-bit shared-memory descriptors are
+    // kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
     const uint32_t idesc = instr_desc_tf32(p.BN), idesc2 = instr_desc_tf32(2 * p.BN);
     const bool leader = elect_one();
-    const uint32_t lo_first = ((a_hi(0) >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
+    const uint32_t lo_first = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
     const uint32_t lo_step = (uint32_t)stage_bytes >> 4;
-    const uint32_t lo_wrap = lo_first + (uint32_t)p.S * lo_step;
     uint32_t lo = lo_first;
-    int s = 0;
-    uint32_t ph = 0;
+    int s = 0, sa = 0;
+    uint32_t ph = 0, pha = 0;
     int tc = 0;
-    const int tail_ksteps = ((a.K - (p.nkb - 1) * BK + 7) >> 3);   // k-steps of the last k-block (1..4)
+    // k-steps of the last k-block: K is permuted inside groups of 16, so whole groups (2 k-steps) are issued
+    const int tail_ksteps = 2 * ((a.K - (p.nkb - 1) * BK + 15) >> 4);
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
-      const int as = tc & 1;
-      const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
+      const int as = p.nacc == 2 ? (tc & 1) : 0;
+      const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
       mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
       const uint32_t d_corr = d_main + (uint32_t)p.BN;
       for (int kb = 0; kb < p.nkb; ++kb) {
-        mbar_wait(ready_a(s), ph);  // A stage written, released, and proxy-fenced by the fence warp
+        mbar_wait(full_a(sa), pha);  // A stage written to tensor memory by all 8 producer warps
         mbar_wait(full_b(s), ph);
         tc_fence_after();
         if (leader && !(p.debug & 16)) {
-          const uint32_t ah = lo, al = lo + (A_TILE_BYTES >> 4), bh = lo + 2 * (A_TILE_BYTES >> 4);
+          const uint32_t ah = tmem_base + (uint32_t)(a_col0 + sa * A_STAGE_COLS), al = ah + 32u;
+          const uint32_t bh = lo;
           const int ksteps = (kb == p.nkb - 1) ? tail_ksteps : 4;
           // B_hi and B_lo are adjacent in the stage ([2*BN rows] x 128 B), and so are the two accumulators
           // ([main | correction] = 2*BN TMEM columns): ONE N = 2*BN instruction computes A_hi*B_hi -> main and
-          // A_hi*B_lo -> correction, reading A_hi once; a second N = BN instruction adds A_lo*B_hi.
-          umma_tf32(d_main, sw128_desc(ah), sw128_desc(bh), idesc2, kb != 0 ? 1u : 0u);
-          umma_tf32(d_corr, sw128_desc(al), sw128_desc(bh), idesc, 1u);
+          // A_hi*B_lo -> correction; a second N = BN instruction adds A_lo*B_hi.
+          umma_tf32_ts(d_main, ah, sw128_desc(bh), idesc2, kb != 0 ? 1u : 0u);
+          umma_tf32_ts(d_corr, al, sw128_desc(bh), idesc, 1u);
 #pragma unroll
           for (int kk = 1; kk < 4; ++kk) {
             if (kk < ksteps) {
-              umma_tf32(d_main, sw128_desc(ah + 2 * kk), sw128_desc(bh + 2 * kk), idesc2, 1u);
-              umma_tf32(d_corr, sw128_desc(al + 2 * kk), sw128_desc(bh + 2 * kk), idesc, 1u);
+              umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + 2 * kk), idesc2, 1u);
+              umma_tf32_ts(d_corr, al + 8u * kk, sw128_desc(bh + 2 * kk), idesc, 1u);
             }
           }
         }
         __syncwarp();
-        if (leader) umma_commit(empty(s));   // frees the smem stage once the MMAs above have read it
+        if (leader) {
+          umma_commit(empty_b(s));    // frees the weight stage once the MMAs above have read it
+          umma_commit(empty_a(sa));   // and the A stage in tensor memory
+        }
         lo += lo_step;
         if (++s == p.S) { s = 0; ph ^= 1u; lo = lo_first; }
+        if (++sa == p.SA) { sa = 0; pha ^= 1u; }
       }
       if (leader) umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
       __syncwarp();
     }
-    (void)lo_wrap;
-  } else {
+  } else if (warp < NUM_EPI_WARPS) {
     // ================================================================ epilogue (warps 0-7)
-    // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w and w+4 form a pair on the same 32 accumulator
-    // rows and split every 32-channel group: `half` 0 drains channels [j0, j0+16), `half` 1 drains [j0+16, j0+32).
-    // Both write their 16 channels into the pair's shared 32 x 128-byte swizzled slab (row-per-thread, conflict-free),
-    // meet on a 64-thread named barrier, and then each stores 16 of the 32 rows with 8 lanes per row, so that every
-    // global store instruction writes four complete 128-byte row segments of the channels-last destination.
+    // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w and w+4 work on the same 32 accumulator rows and
+    // take the 16-channel groups [g_begin, g_end) each.  Phase 1 (drain): per group tcgen05.ld main + correction,
+    // add, + bias (+ channel add), Relu, and park the row in the warp's private slab (row per thread, 16-byte chunks
+    // XOR-swizzled by row: conflict-free); then the accumulator stage goes back to the MMA warp.  Phase 2 (store):
+    // consecutive lanes take consecutive 16-byte chunks of a row, so the global stores cover whole sectors of the
+    // channels-last destination (which may be a channel slice of a Concat result).
     const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t slab = epi_staging + (uint32_t)quarter * EPI_SLAB_BYTES;
-    const uint32_t pair_bar = 1u + (uint32_t)quarter;   // named barriers 1..4 (0 is __syncthreads)
+    const int G = p.BN >> 4;
+    const int g_begin = half ? (G + 1) >> 1 : 0, g_end = half ? G : (G + 1) >> 1;
+    const int ng = g_end - g_begin;            // 0..4 groups of 16 channels
+    const int nchunk = ng * 4;                 // 16-byte chunks per slab row
+    const uint32_t slab = epi_slabs + (uint32_t)(warp * 32 * p.slab_pitch);
     const bool has_add = a.chan_add != nullptr, do_relu = a.relu != 0;
+    const uint32_t my_row = slab + (uint32_t)(lane * p.slab_pitch);
+    const uint32_t rcp = nchunk ? (65536u + (uint32_t)nchunk - 1u) / (uint32_t)nchunk : 0u;   // L / nchunk for L < 512
     int tc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
-      const int as = tc & 1;
-      const uint32_t aph = (uint32_t)(tc >> 1) & 1u;
+      const int as = p.nacc == 2 ? (tc & 1) : 0;
+      const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
       const int p0 = (t / p.n_tiles_n) * BM;
       const int m0 = (t % p.n_tiles_n) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * p.BN);
-      for (int j0 = 0; j0 < p.BN; j0 += 32) {
-        const int width = min(32, p.BN - j0);   // 32, or 16 for the last group when BN % 32 == 16
-        const int h = half * 16;
-        if (h < width) {
-          uint32_t acc[16], cor[16];
-          tmem_ld16(t_main + (uint32_t)(j0 + h), acc);
-          tmem_ld16(t_main + (uint32_t)(p.BN + j0 + h), cor);
-          tmem_ld_wait();
+      for (int g = g_begin; g < g_end; ++g) {
+        uint32_t acc[16], cor[16];
+        tmem_ld16(t_main + (uint32_t)(g * 16), acc);
+        tmem_ld16(t_main + (uint32_t)(p.BN + g * 16), cor);
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint32_t off = 4u * (uint32_t)(m0 + j0 + h + q * 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + off));
-            if (has_add)
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + off));
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-            float o[4];
+        for (int q = 0; q < 4; ++q) {
+          float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const uint32_t off = 4u * (uint32_t)(m0 + g * 16 + q * 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + off));
+          if (has_add)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + off));
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+          float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = q * 4 + e;
-              float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
-              val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
-              if (has_add) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
-              if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
-              o[e] = val;
-            }
-            const int c = (h >> 2) + q;   // 16-byte chunk within the 128-byte slab row
-            const uint32_t addr = slab + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 4 + e;
+            float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
+            val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
+            if (has_add) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
+            if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
+            o[e] = val;
           }
+          const int c = (g - g_begin) * 4 + q;   // 16-byte chunk within the slab row
+          const uint32_t addr = my_row + (uint32_t)((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // both halves of the slab are written
-        const int c = lane & 7;
-        const int m = m0 + j0 + c * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = half * 16 + i * 4 + (lane >> 3);
-          const int prow = p0 + quarter * 32 + rr;
-          if (c * 4 < width && prow < p.P && m < a.M && !(p.debug & 4)) {
-            float4 val;
-            const uint32_t addr = slab + (uint32_t)rr * 128u + (uint32_t)((c ^ (rr & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
-            float* dst = a.y + (long long)prow * a.ldy + m;
-            if (p.vec_store && m + 4 <= a.M) {
-              *reinterpret_cast<float4*>(dst) = val;
-            } else {
-              dst[0] = val.x;
-              if (m + 1 < a.M) dst[1] = val.y;
-              if (m + 2 < a.M) dst[2] = val.z;
-              if (m + 3 < a.M) dst[3] = val.w;
-            }
-          }
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // the slab is rewritten by the next channel group
       }
-      // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
+      // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp before storing
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(as));
+      const int total = 32 * nchunk;
+      for (int L = lane; L < total; L += 32) {
+        const int rr = (int)(((uint32_t)L * rcp) >> 16);
+        const int c = L - rr * nchunk;
+        const int prow = p0 + quarter * 32 + rr;
+        const int m = m0 + g_begin * 16 + c * 4;
+        if (prow < p.P && m < a.M && !(p.debug & 4)) {
+          float4 val;
+          const uint32_t addr = slab + (uint32_t)(rr * p.slab_pitch) + (uint32_t)((c ^ (rr & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
+          float* dst = a.y + (long long)prow * a.ldy + m;
+          if (p.vec_store && m + 4 <= a.M) {
+            *reinterpret_cast<float4*>(dst) = val;
+          } else {
+            dst[0] = val.x;
+            if (m + 1 < a.M) dst[1] = val.y;
+            if (m + 2 < a.M) dst[2] = val.z;
+            if (m + 3 < a.M) dst[3] = val.w;
+          }
+        }
+      }
+      __syncwarp();   // the slab is rewritten by the next tile's drain
     }
   }
 
@@ -587,15 +583,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   __syncthreads();
   if (warp == TMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, 512u);
   }
 }
 
 // Weight preparation: w [M][ldw] (K valid floats per row) -> out [2*Mpad][Kpad]: tf32 hi rows, then lo rows.
+// Position 16g + j of an output row holds k = 16g + perm(j), the order in which tcgen05.st.16x256b lays the
+// activations' 16-float groups out in tensor-memory columns (see tmem_st_16x256b_x2).
 __global__ void tc_split_weights_kernel(const float* __restrict__ w, int M, int K, int ldw, float* __restrict__ out, int Mpad, int Kpad) {
   const long long total = (long long)Mpad * Kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int m = (int)(i / Kpad), k = (int)(i - (long long)m * Kpad);
+    const int m = (int)(i / Kpad), kp = (int)(i - (long long)m * Kpad);
+    const int j = kp & 15;
+    const int k = (kp & ~15) + (j < 8 ? 4 * (j >> 1) + (j & 1) : 4 * ((j - 8) >> 1) + 2 + (j & 1));
     float x = 0.f;
     if (m < M && k < K) x = w[(long long)m * ldw + k];
     const float hi = tf32_rna(x);
@@ -685,10 +685,17 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   const long long tiles = ((P + BM - 1) / BM) * p.n_tiles_n;
   if (tiles >= (1ll << 31)) B200_FAIL(B200_EUNSUPPORTED, "too many tiles");
   p.total_tiles = (int)tiles;
-  p.tmem_cols = 32;
-  while (p.tmem_cols < 4 * p.BN) p.tmem_cols <<= 1;   // 2 stages x (main + correction)
-  const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.BN * BK * 4;
-  const int fixed = 1024 + EPI_STAGING_BYTES + 8 * p.Mpad + 8 * (4 * MAX_STAGES + 5 + 2 * MAX_RAW);
+  // tensor memory: accumulator stages {main | correction} x BN, then A stages of 64 columns
+  static const int force_nacc = [] { const char* e = getenv("B200_TC_NACC"); return e ? atoi(e) : 0; }();   // experiments only
+  p.nacc = (4 * p.BN + 2 * A_STAGE_COLS <= 512) ? 2 : 1;
+  if (force_nacc == 1) p.nacc = 1;
+  p.SA = (512 - p.nacc * 2 * p.BN) / A_STAGE_COLS;
+  if (p.SA > MAX_A_STAGES) p.SA = MAX_A_STAGES;
+  // shared memory: weight ring, raw A ring (pointwise mode), epilogue slabs, per-channel constants, barriers
+  const int stage_bytes = 2 * p.BN * BK * 4;
+  const int groups_per_warp = ((p.BN >> 4) + 1) >> 1;
+  p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
+  const int fixed = 1024 + NUM_EPI_WARPS * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW);
   // Pointwise layers (1x1, stride 1, no padding): im2col row p IS input pixel p, so the A operand is a plain 2-D
   // matrix [P][C] and TMA can stream it; these layers are HBM-bound and want many bytes in flight.
   static const int no_atma = [] { const char* e = getenv("B200_TC_NO_ATMA"); return e ? atoi(e) : 0; }();
@@ -696,15 +703,16 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.R = 0;
   int S = (SMEM_MAX - fixed) / stage_bytes;
   if (S > MAX_STAGES) S = MAX_STAGES;
+  if (S > p.nkb + 1) S = p.nkb + 1;   // a ring deeper than a tile's k-blocks (+1 for the next tile) buys nothing
+  if (S < 2) S = 2;
   if (p.a_tma) {
     if (S > 3) S = 3;
-    if (S > 2 && stage_bytes >= 64 * 1024) S = 2;
     int R = (SMEM_MAX - fixed - S * stage_bytes) / A_TILE_BYTES;
     if (R > MAX_RAW) R = MAX_RAW;
-    if (S < 2 || R < 2) { p.a_tma = 0; S = (SMEM_MAX - fixed) / stage_bytes; if (S > MAX_STAGES) S = MAX_STAGES; }
+    if (R < 2) p.a_tma = 0;
     else p.R = R;
   }
-  if (S < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 stages (BN=%d)", p.BN);
+  if ((size_t)S * stage_bytes + fixed > (size_t)SMEM_MAX) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 weight stages (BN=%d)", p.BN);
   p.S = S;
   const size_t smem = (size_t)S * stage_bytes + (size_t)p.R * A_TILE_BYTES + fixed;
 
