@@ -9,7 +9,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_HERE, "lib", "libb200rt.so")   # B200RT_LIB: A/B builds (tools/exp)
 
 PAD_VALID, PAD_SAME_UPPER, PAD_SAME_LOWER, PAD_NOTSET = 0, 1, 2, 3
 ERR_NAMES = {-1: "EINVAL", -2: "EUNSUPPORTED", -3: "ECUDA", -4: "ENOMEM", -5: "EPARSE", -6: "ENODEVICE"}

@@ -57,11 +57,12 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMA_WARP = 8;
 constexpr int MMA_WARP = 9;
 constexpr int ATMA_WARP = 10;   // pointwise layers: issues the TMA loads of the raw A tiles
-constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_PROD_WARPS = 16;  // two sets of 8: a set fills every other k-block
+constexpr int PROD_SET_WARPS = 8;
 constexpr int PROD_WARP0 = 12;  // a multiple of 4: producer warp w writes TMEM lanes 32*(w%4)..
-constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 640
+constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 896
 constexpr int ROWS_PER_THREAD = 4;         // rows lane/4 + 8i of the warp's 32-row quarter
-constexpr int PREFETCH = 3;                // k-blocks of A loads in flight per producer thread
+constexpr int PREFETCH = 2;                // k-blocks of A loads in flight per producer thread (4 per SM-wide k-block stream)
 constexpr int A_STAGE_COLS = 64;           // TMEM columns per A stage: hi 32 | lo 32
 constexpr int MAX_A_STAGES = 4;
 constexpr int SMEM_MAX = 227 * 1024;
@@ -202,24 +203,22 @@ __device__ __forceinline__ float tf32_rna(float x) {
 __device__ __forceinline__ float split_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float split_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) + 0x1000u); }
 
-// A producer's four 16-byte chunks (rows lane/4 + 8i of its 32-row quarter), split into hi / lo
-struct SplitRows { float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD]; };
-__device__ __forceinline__ void split_rows(const float4 (&x)[ROWS_PER_THREAD], SplitRows& o) {
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    o.hi[i].x = split_hi(x[i].x); o.hi[i].y = split_hi(x[i].y); o.hi[i].z = split_hi(x[i].z); o.hi[i].w = split_hi(x[i].w);
-    o.lo[i].x = split_lo(x[i].x, o.hi[i].x); o.lo[i].y = split_lo(x[i].y, o.hi[i].y);
-    o.lo[i].z = split_lo(x[i].z, o.hi[i].z); o.lo[i].w = split_lo(x[i].w, o.hi[i].w);
-  }
-}
-// ... and written to the warp's part of an A stage in tensor memory: hi -> columns [0,32), lo -> [32,64) of the stage;
-// t_stage = lane 32*quarter, column of the warp's 16-column half.  Two 16-lane halves: rows i = 2j, 2j+1.
-__device__ __forceinline__ void store_rows(uint32_t t_stage, const SplitRows& o) {
+// A producer's four 16-byte chunks (rows lane/4 + 8i of its 32-row quarter) are split into hi / lo and written to the
+// warp's part of an A stage in tensor memory: hi -> columns [0,32), lo -> [32,64) of the stage; t_stage = lane
+// 32*quarter, column of the warp's 16-column half.  Two 16-lane halves: rows i = 2j, 2j+1 (split per half, so only 16
+// temporaries are live).
+__device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[ROWS_PER_THREAD]) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
+    const float4 a = x[2 * j], b = x[2 * j + 1];
+    float4 ah, bh, al, bl;
+    ah.x = split_hi(a.x); ah.y = split_hi(a.y); ah.z = split_hi(a.z); ah.w = split_hi(a.w);
+    bh.x = split_hi(b.x); bh.y = split_hi(b.y); bh.z = split_hi(b.z); bh.w = split_hi(b.w);
     const uint32_t ta = t_stage + ((uint32_t)(j * 16) << 16);
-    tmem_st_16x256b_x2(ta, o.hi[2 * j].x, o.hi[2 * j].y, o.hi[2 * j + 1].x, o.hi[2 * j + 1].y, o.hi[2 * j].z, o.hi[2 * j].w, o.hi[2 * j + 1].z, o.hi[2 * j + 1].w);
-    tmem_st_16x256b_x2(ta + 32u, o.lo[2 * j].x, o.lo[2 * j].y, o.lo[2 * j + 1].x, o.lo[2 * j + 1].y, o.lo[2 * j].z, o.lo[2 * j].w, o.lo[2 * j + 1].z, o.lo[2 * j + 1].w);
+    tmem_st_16x256b_x2(ta, ah.x, ah.y, bh.x, bh.y, ah.z, ah.w, bh.z, bh.w);
+    al.x = split_lo(a.x, ah.x); al.y = split_lo(a.y, ah.y); al.z = split_lo(a.z, ah.z); al.w = split_lo(a.w, ah.w);
+    bl.x = split_lo(b.x, bh.x); bl.y = split_lo(b.y, bh.y); bl.z = split_lo(b.z, bh.z); bl.w = split_lo(b.w, bh.w);
+    tmem_st_16x256b_x2(ta + 32u, al.x, al.y, bl.x, bl.y, al.z, al.w, bl.z, bl.w);
   }
 }
 
@@ -245,6 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 4);
   auto raw_full = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + r); };
   auto raw_empty = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + MAX_RAW + r); };
+  const uint32_t ktab = (raw_empty(MAX_RAW) + 15u) & ~15u;   // gather mode: nkb x 8 entries {delta, r, s, valid mask}
   const int a_col0 = p.nacc * 2 * p.BN;   // first TMEM column of the A stages
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -257,12 +257,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(sadd + 4u * m), "f"(c) : "memory");
   }
 
+  // gather mode: what a 16-byte chunk of a k-block means is the same for every tile, so the (r, s, c) decode is
+  // done once per CTA: entry (kb, chunk) = {element offset of tap (r, s) channel c from a row's base, r, s,
+  // 0x01010101 when k < K else 0}
+  if (!p.a_tma) {
+    for (int e = threadIdx.x; e < p.nkb * 8; e += NTHREADS) {
+      const int k = e * 4;
+      const int tap = k / a.C, c = k - tap * a.C;
+      const int r = tap / a.KW, sx = tap - r * a.KW;
+      const bool ok = k < a.K;
+      const int delta = ok ? (r * a.W + sx) * a.ldx + c : 0;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ktab + 16u * e), "r"(delta), "r"(ok ? r : 0), "r"(ok ? sx : 0),
+                   "r"(ok ? 0x01010101u : 0u)
+                   : "memory");
+    }
+  }
+
   if (warp == TMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < p.S; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-      for (int s = 0; s < p.SA; ++s) { mbar_init(full_a(s), NUM_PROD_WARPS); mbar_init(empty_a(s), 1); }
+      for (int s = 0; s < p.SA; ++s) { mbar_init(full_a(s), PROD_SET_WARPS); mbar_init(empty_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
-      for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), NUM_PROD_WARPS); }
+      for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), PROD_SET_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -275,18 +291,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp >= PROD_WARP0) {
-    // ================================================================ A producers (8 warps)
+    // ================================================================ A producers (16 warps, two sets of 8)
     // Warp w may only write TMEM lanes 32*(w % 4) .. +31: it owns rows 32*quarter + 8*i + lane/4 (i = 0..3) of the
-    // tile and the 16-byte chunk 4*khalf + lane%4 of each 128-byte k-block row.
+    // tile and the 16-byte chunk 4*khalf + lane%4 of each 128-byte k-block row.  The two sets take alternate
+    // k-blocks of the CTA's k-block stream (SA and R are even, so a set always meets the same A stages / raw
+    // slots): a single warp's instruction stream was the pacing resource with 8 producer warps.
     const int pw = warp - PROD_WARP0;
-    const int quarter = pw & 3, khalf = pw >> 2;
+    const int quarter = pw & 3, khalf = (pw >> 2) & 1, kpar = pw >> 3;
     const int chunk = khalf * 4 + (lane & 3);
     const int rsub = lane >> 2;
     int my_tiles = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) ++my_tiles;
-    const int items = my_tiles * p.nkb;
+    const int items = my_tiles * p.nkb;   // k-blocks of this CTA; this warp handles idx = kpar, kpar + 2, ...
     // TMEM address of this warp's part of A stage 0: lane 32*quarter, column a_col0 + 16*khalf
     const uint32_t t_a0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a_col0 + khalf * 16);
+    int sa = kpar;          // A stage of the current k-block (idx % SA)
+    uint32_t ph = 0;        // its phase
 
     if (p.a_tma) {
       // ---- TMA-fed mode (pointwise layers): the raw fp32 tile of each k-block is in shared memory (128B-swizzled
@@ -297,36 +317,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         const int row = quarter * 32 + i * 8 + rsub;
         off[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
       }
-      int sa = 0, r = 0;
-      uint32_t ph = 0, rph = 0;
-      for (int idx = 0; idx < items; ++idx) {
+      int r = kpar;
+      uint32_t rph = 0;
+      for (int idx = kpar; idx < items; idx += 2) {
         mbar_wait(raw_full(r), rph);
         const uint32_t raw = raw_ring + (uint32_t)r * A_TILE_BYTES;
         float4 x[ROWS_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i)
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
-        SplitRows hl;
-        split_rows(x, hl);
+        // Split first: every split instruction consumes loaded values, so once they have issued the shared-memory
+        // reads are complete and the raw slot can go back to the TMA warp (releasing it right after issuing the
+        // ld.shared let the next TMA write overtake the reads).
+        float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          hi[i].x = split_hi(x[i].x); hi[i].y = split_hi(x[i].y); hi[i].z = split_hi(x[i].z); hi[i].w = split_hi(x[i].w);
+          lo[i].x = split_lo(x[i].x, hi[i].x); lo[i].y = split_lo(x[i].y, hi[i].y);
+          lo[i].z = split_lo(x[i].z, hi[i].z); lo[i].w = split_lo(x[i].w, hi[i].w);
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(raw_empty(r));   // the raw slot has been read (values are in registers)
-        if (++r == p.R) { r = 0; rph ^= 1u; }
+        if (lane == 0) mbar_arrive(raw_empty(r));
+        r += 2;
+        if (r >= p.R) { r -= p.R; rph ^= 1u; }
         mbar_wait(empty_a(sa), ph ^ 1u);
         tc_fence_after();
-        if (!(p.debug & 32)) store_rows(t_a0 + (uint32_t)(sa * A_STAGE_COLS), hl);
+        if (!(p.debug & 32)) {
+          const uint32_t t_stage = t_a0 + (uint32_t)(sa * A_STAGE_COLS);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t ta = t_stage + ((uint32_t)(j * 16) << 16);
+            tmem_st_16x256b_x2(ta, hi[2 * j].x, hi[2 * j].y, hi[2 * j + 1].x, hi[2 * j + 1].y, hi[2 * j].z, hi[2 * j].w, hi[2 * j + 1].z, hi[2 * j + 1].w);
+            tmem_st_16x256b_x2(ta + 32u, lo[2 * j].x, lo[2 * j].y, lo[2 * j + 1].x, lo[2 * j + 1].y, lo[2 * j].z, lo[2 * j].w, lo[2 * j + 1].z, lo[2 * j + 1].w);
+          }
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_a(sa));
-        if (++sa == p.SA) { sa = 0; ph ^= 1u; }
+        sa += 2;
+        if (sa >= p.SA) { sa -= p.SA; ph ^= 1u; }
       }
     } else {
-      // ---- register gather.  Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, a base pointer (tap
-      // (0,0), channel 0) and two separable validity masks (bit 8*i+r: input row h0+r inside the image; bit 8*i+s:
-      // column w0+s inside).  Per k-block the chunk's (r, s, c) is decoded once (multiply-high division) into one
-      // element offset shared by all rows, so a load costs an add, a mask test and the LDG.
-      int l_tile = blockIdx.x, l_kb = 0;   // load cursor
-      const float* base[ROWS_PER_THREAD];
+      // ---- register gather.  Per tile each thread fixes, for its ROWS_PER_THREAD im2col rows, an element offset
+      // (tap (0,0), channel 0) and two separable validity masks (bit 8*i+r: input row h0+r inside the image; bit
+      // 8*i+s: column w0+s inside).  Per k-block the chunk's (r, s, offset) comes from the per-CTA table, shared by
+      // all rows, so a load costs an add, a mask test and the LDG.
+      int l_tile = blockIdx.x, l_kb = kpar;   // load cursor
+      while (l_kb >= p.nkb) { l_kb -= p.nkb; l_tile += gridDim.x; }
+      int base[ROWS_PER_THREAD];              // element offsets from a.x (< 2^31, checked on the host)
       uint32_t hmask = 0, wmask = 0;
       auto set_tile = [&](int tile) {
         // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
@@ -347,7 +386,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           const int ho = hsum - ch * a.Ho;
           const int n = n0 + ch;
           const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
-          base[i] = a.x + ((long long)n * a.H * a.W + (long long)h0 * a.W + w0) * a.ldx;
+          base[i] = ((n * a.H + h0) * a.W + w0) * a.ldx;   // may be "negative" for padded taps: never dereferenced then
           // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
           const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
           const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
@@ -359,48 +398,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       };
       float4 v[PREFETCH][ROWS_PER_THREAD];
       auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
-        const int k = l_kb * BK + chunk * 4;
-        const int tap = p.magicC ? (int)__umulhi((unsigned)k, p.magicC) : k;      // k / C
-        const int c = k - tap * a.C;
-        const int r = p.magicKW ? (int)__umulhi((unsigned)tap, p.magicKW) : tap;  // tap / KW
-        const int sx = tap - r * a.KW;
-        const int delta = (r * a.W + sx) * a.ldx + c;
-        const uint32_t m = (k < a.K) ? ((hmask >> r) & (wmask >> sx)) : 0u;   // bit 8*i: row i valid for this tap
+        uint32_t delta, r, sx, vm;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(delta), "=r"(r), "=r"(sx), "=r"(vm) : "r"(ktab + 16u * (uint32_t)(l_kb * 8 + chunk)));
+        const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(base[i] + delta));
+          if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
         }
-        if (++l_kb == p.nkb) {
-          l_kb = 0;
-          l_tile += gridDim.x;
+        l_kb += 2;
+        if (l_kb >= p.nkb) {
+          do { l_kb -= p.nkb; l_tile += gridDim.x; } while (l_kb >= p.nkb);
           if (l_tile < p.total_tiles) set_tile(l_tile);
         }
       };
-      if (items > 0) set_tile(l_tile);
+      const int my_items = (items - kpar + 1) >> 1;   // k-blocks this warp handles
+      if (my_items > 0) set_tile(l_tile);
 #pragma unroll
       for (int d = 0; d < PREFETCH; ++d)
-        if (d < items) issue(v[d]);
+        if (d < my_items) issue(v[d]);
 
-      int sa = 0;
-      uint32_t ph = 0;
-      for (int base_i = 0; base_i < items; base_i += PREFETCH) {
+      for (int base_i = 0; base_i < my_items; base_i += PREFETCH) {
 #pragma unroll
         for (int d = 0; d < PREFETCH; ++d) {
-          const int idx = base_i + d;
-          if (idx < items) {
-            // split in registers first (independent of the stage), then wait for the stage and store
-            SplitRows hl;
-            split_rows(v[d], hl);
+          const int it = base_i + d;
+          if (it < my_items) {
             mbar_wait(empty_a(sa), ph ^ 1u);   // the MMAs that read this A stage have completed
             tc_fence_after();
-            if (!(p.debug & 32)) store_rows(t_a0 + (uint32_t)(sa * A_STAGE_COLS), hl);
-            if (idx + PREFETCH < items) issue(v[d]);   // next loads go out before the store wait
+            if (!(p.debug & 32)) split_store(t_a0 + (uint32_t)(sa * A_STAGE_COLS), v[d]);
+            if (it + PREFETCH < my_items) issue(v[d]);   // next loads go out before the store wait
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(sa));
-            if (++sa == p.SA) { sa = 0; ph ^= 1u; }
+            sa += 2;
+            if (sa >= p.SA) { sa -= p.SA; ph ^= 1u; }
           }
         }
       }
@@ -639,10 +671,10 @@ int tc_supported(const ConvArgs& a) {
   if (a.M < 1 || a.K < 8) return B200_EUNSUPPORTED;
   if (a.KH > 8 || a.KW > 8 || a.pt > 15 || a.pl > 15 || ROWS_PER_THREAD > 4) return B200_EUNSUPPORTED;                  // 16-bit validity masks per row
   if (a.Ho + BM >= 65536 || a.Wo + BM >= 65536) return B200_EUNSUPPORTED;                       // multiply-high division range
-  if (a.K >= 65536 || a.C >= 65536) return B200_EUNSUPPORTED;                                 // multiply-high division range
+  if (a.K > 12288 || a.C >= 65536) return B200_EUNSUPPORTED;                                  // k decode table: 128 B per k-block in shared memory
   if ((long long)(a.KH + 1) * a.W * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;           // 32-bit tap offsets
   const long long P = (long long)a.N * a.Ho * a.Wo, in_pix = (long long)a.N * a.H * a.W;
-  if (P >= (1ll << 31) - BM || in_pix >= (1ll << 31)) return B200_EUNSUPPORTED;  // 32-bit pixel indices in the producer
+  if (P >= (1ll << 31) - BM || (in_pix + (long long)a.W * 16) * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;  // 32-bit element offsets in the producer
   return 0;
 }
 
@@ -691,16 +723,18 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   if (force_nacc == 1) p.nacc = 1;
   p.SA = (512 - p.nacc * 2 * p.BN) / A_STAGE_COLS;
   if (p.SA > MAX_A_STAGES) p.SA = MAX_A_STAGES;
+  p.SA &= ~1;   // the two producer sets alternate k-blocks: even stage counts keep a set on its own stages
   // shared memory: weight ring, raw A ring (pointwise mode), epilogue slabs, per-channel constants, barriers
   const int stage_bytes = 2 * p.BN * BK * 4;
   const int groups_per_warp = ((p.BN >> 4) + 1) >> 1;
   p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
-  const int fixed = 1024 + NUM_EPI_WARPS * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW);
+  int fixed = 1024 + NUM_EPI_WARPS * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW) + 16;
   // Pointwise layers (1x1, stride 1, no padding): im2col row p IS input pixel p, so the A operand is a plain 2-D
   // matrix [P][C] and TMA can stream it; these layers are HBM-bound and want many bytes in flight.
   static const int no_atma = [] { const char* e = getenv("B200_TC_NO_ATMA"); return e ? atoi(e) : 0; }();
   p.a_tma = (!no_atma && a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.pt == 0 && a.pl == 0 && a.H == a.Ho && a.W == a.Wo) ? 1 : 0;
   p.R = 0;
+  if (!p.a_tma) fixed += 128 * p.nkb;   // gather mode: the per-CTA k decode table
   int S = (SMEM_MAX - fixed) / stage_bytes;
   if (S > MAX_STAGES) S = MAX_STAGES;
   if (S > p.nkb + 1) S = p.nkb + 1;   // a ring deeper than a tile's k-blocks (+1 for the next tile) buys nothing
@@ -709,8 +743,9 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
     if (S > 3) S = 3;
     int R = (SMEM_MAX - fixed - S * stage_bytes) / A_TILE_BYTES;
     if (R > MAX_RAW) R = MAX_RAW;
-    if (R < 2) p.a_tma = 0;
-    else p.R = R;
+    R &= ~1;   // same for the raw ring
+    if (R < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for the raw A ring (BN=%d)", p.BN);
+    p.R = R;
   }
   if ((size_t)S * stage_bytes + fixed > (size_t)SMEM_MAX) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 weight stages (BN=%d)", p.BN);
   p.S = S;
