@@ -223,6 +223,7 @@ __device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+template <bool HAS_ADD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -541,9 +542,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     const int ng = g_end - g_begin;            // 0..4 groups of 16 channels
     const int nchunk = ng * 4;                 // 16-byte chunks per slab row
     const uint32_t slab = epi_slabs + (uint32_t)(warp * 32 * p.slab_pitch);
-    const bool has_add = a.chan_add != nullptr, do_relu = a.relu != 0;
+    const bool do_relu = a.relu != 0;
     const uint32_t my_row = slab + (uint32_t)(lane * p.slab_pitch);
-    const uint32_t rcp = nchunk ? (65536u + (uint32_t)nchunk - 1u) / (uint32_t)nchunk : 0u;   // L / nchunk for L < 512
+    const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;   // XOR swizzle of this lane's slab row
+    const bool fast_store = p.vec_store && (a.M & 3) == 0;   // every 16-byte chunk is all-or-nothing
     int tc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
       const int as = p.nacc == 2 ? (tc & 1) : 0;
@@ -558,13 +560,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         tmem_ld16(t_main + (uint32_t)(g * 16), acc);
         tmem_ld16(t_main + (uint32_t)(p.BN + g * 16), cor);
         tmem_ld_wait();
+        const uint32_t boff = 4u * (uint32_t)(m0 + g * 16);
+        const uint32_t crow = my_row + ((uint32_t)(g - g_begin) << 6);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const uint32_t off = 4u * (uint32_t)(m0 + g * 16 + q * 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + off));
-          if (has_add)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + off));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + boff + 16u * q));
+          if (HAS_ADD)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + boff + 16u * q));
           const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
           const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
           float o[4];
@@ -573,37 +576,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
             const int j = q * 4 + e;
             float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
             val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
-            if (has_add) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
+            if (HAS_ADD) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
             if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
             o[e] = val;
           }
-          const int c = (g - g_begin) * 4 + q;   // 16-byte chunk within the slab row
-          const uint32_t addr = my_row + (uint32_t)((c ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+          // 16-byte chunk (g - g_begin) * 4 + q of the slab row, XOR-swizzled by the row
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((crow + 16u * q) ^ lane_sw), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
         }
       }
       // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp before storing
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(as));
-      const int total = 32 * nchunk;
-      for (int L = lane; L < total; L += 32) {
-        const int rr = (int)(((uint32_t)L * rcp) >> 16);
-        const int c = L - rr * nchunk;
-        const int prow = p0 + quarter * 32 + rr;
-        const int m = m0 + g_begin * 16 + c * 4;
-        if (prow < p.P && m < a.M && !(p.debug & 4)) {
-          float4 val;
-          const uint32_t addr = slab + (uint32_t)(rr * p.slab_pitch) + (uint32_t)((c ^ (rr & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
-          float* dst = a.y + (long long)prow * a.ldy + m;
-          if (p.vec_store && m + 4 <= a.M) {
-            *reinterpret_cast<float4*>(dst) = val;
-          } else {
-            dst[0] = val.x;
-            if (m + 1 < a.M) dst[1] = val.y;
-            if (m + 2 < a.M) dst[2] = val.z;
-            if (m + 3 < a.M) dst[3] = val.w;
+      const int row0 = p0 + quarter * 32;                 // first pixel of this warp's 32 rows
+      const int rows_valid = min(32, p.P - row0);          // <= 0 for a quarter past the end
+      const int mbase = m0 + g_begin * 16;
+      if (p.debug & 4) {
+      } else if (fast_store) {
+        // chunk columns in power-of-two blocks (16, 8 or 4 wide; 12 = 8 + 4): a lane keeps its chunk column and walks
+        // down the rows, so an iteration is a bounds test, the swizzle, LDS.128, STG.128 and two pointer adds
+        int cdone = 0;
+        while (cdone < nchunk) {
+          const int w = (nchunk - cdone >= 16) ? 16 : (nchunk - cdone >= 8) ? 8 : 4;
+          const int lw = (w == 16) ? 4 : (w == 8) ? 3 : 2;
+          const int c = cdone + (lane & (w - 1));
+          const int step = 32 >> lw;                        // rows per iteration
+          int rr = lane >> lw;
+          const int m = mbase + c * 4;
+          const int rows_ok = (m < a.M) ? rows_valid : 0;
+          float* dst = a.y + (long long)(row0 + rr) * a.ldy + m;
+          const long long dstep = (long long)step * a.ldy;
+          uint32_t src = slab + (uint32_t)(rr * p.slab_pitch) + ((uint32_t)c << 4);
+          const uint32_t sstep = (uint32_t)(step * p.slab_pitch);
+#pragma unroll 4
+          for (int it = 0; it < (1 << lw); ++it) {
+            if (rr < rows_ok) {
+              float4 val;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(src ^ ((uint32_t)(rr & 7) << 4)));
+              *reinterpret_cast<float4*>(dst) = val;
+            }
+            rr += step; dst += dstep; src += sstep;
+          }
+          cdone += w;
+        }
+      } else {
+        const uint32_t rcp = nchunk ? (65536u + (uint32_t)nchunk - 1u) / (uint32_t)nchunk : 0u;   // L / nchunk for L < 512
+        const int total = 32 * nchunk;
+        for (int L = lane; L < total; L += 32) {
+          const int rr = (int)(((uint32_t)L * rcp) >> 16);
+          const int c = L - rr * nchunk;
+          const int m = mbase + c * 4;
+          if (rr < rows_valid && m < a.M) {
+            float4 val;
+            const uint32_t addr = slab + (uint32_t)(rr * p.slab_pitch) + (uint32_t)((c ^ (rr & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
+            float* dst = a.y + (long long)(row0 + rr) * a.ldy + m;
+            if (p.vec_store && m + 4 <= a.M) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              dst[0] = val.x;
+              if (m + 1 < a.M) dst[1] = val.y;
+              if (m + 2 < a.M) dst[2] = val.z;
+              if (m + 3 < a.M) dst[3] = val.w;
+            }
           }
         }
       }
@@ -763,7 +798,8 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   B200_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -782,7 +818,8 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
                      : CUDA_ERROR_NOT_SUPPORTED;
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
   }
-  conv_tc_kernel<<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  if (a.chan_add) conv_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  else conv_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
