@@ -3,6 +3,7 @@
 // use 128-bit accesses along the channel axis whenever C, the pitches and the base pointers allow it,
 // grid-stride loops sized in multiples of the SM count, and warp-shuffle reductions.
 #include <cfloat>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -114,6 +115,55 @@ __global__ void maxpool_kernel(PoolArgs a) {
     float* py = a.y + (long long)pix * a.ldy;
     if (VEC) *reinterpret_cast<float4*>(py + c * 4) = m;
     else py[c] = m.x;
+  }
+}
+
+// The SqueezeNet pools (3x3, stride 2): consecutive output rows share an input row, so a thread walks down a strip
+// of output rows for one (image, output column, 4 channels) and carries the shared row's column-max along: 6 loads
+// per output instead of 9.  max is exact, so any association gives the reference's bits (zero-filled padding taps
+// and the -FLT_MAX fold start included).
+constexpr int kPoolStrip = 14;   // output rows per thread
+__global__ void maxpool3x3s2_kernel(PoolArgs a, int strips) {
+  const int CV = a.C / 4;
+  const unsigned total = (unsigned)a.N * strips * a.Wo * CV;   // < 2^31, checked by the launcher
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV);
+    unsigned t = i / CV;
+    const int wo = (int)(t % a.Wo);
+    t /= a.Wo;
+    const int strip = (int)(t % strips);
+    const int n = (int)(t / strips);
+    const int ho_begin = strip * kPoolStrip, ho_end = min(a.Ho, ho_begin + kPoolStrip);
+    const int w0 = wo * 2 - a.pl;
+    const float* img = a.x + (long long)n * a.H * a.W * a.ldx + c * 4;
+    const bool in0 = (unsigned)w0 < (unsigned)a.W, in1 = (unsigned)(w0 + 1) < (unsigned)a.W, in2 = (unsigned)(w0 + 2) < (unsigned)a.W;
+    auto rowmax = [&](int h) {
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;   // padded taps read as 0.0, like the reference
+      if ((unsigned)h < (unsigned)a.H) {
+        const float* px = img + ((long long)h * a.W + w0) * a.ldx;
+        if (in0) v0 = ldg4(px);
+        if (in1) v1 = ldg4(px + a.ldx);
+        if (in2) v2 = ldg4(px + 2 * a.ldx);
+      }
+      float4 m;
+      m.x = fmaxf(fmaxf(v0.x, v1.x), v2.x); m.y = fmaxf(fmaxf(v0.y, v1.y), v2.y);
+      m.z = fmaxf(fmaxf(v0.z, v1.z), v2.z); m.w = fmaxf(fmaxf(v0.w, v1.w), v2.w);
+      return m;
+    };
+    float4 carry = rowmax(ho_begin * 2 - a.pt);
+    float* py = a.y + (((long long)n * a.Ho + ho_begin) * a.Wo + wo) * a.ldy + c * 4;
+    const long long ystep = (long long)a.Wo * a.ldy;
+#pragma unroll 2
+    for (int ho = ho_begin; ho < ho_end; ++ho) {
+      const int h0 = ho * 2 - a.pt;
+      const float4 r1 = rowmax(h0 + 1), r2 = rowmax(h0 + 2);
+      float4 m;
+      m.x = fmaxf(-FLT_MAX, fmaxf(fmaxf(carry.x, r1.x), r2.x)); m.y = fmaxf(-FLT_MAX, fmaxf(fmaxf(carry.y, r1.y), r2.y));
+      m.z = fmaxf(-FLT_MAX, fmaxf(fmaxf(carry.z, r1.z), r2.z)); m.w = fmaxf(-FLT_MAX, fmaxf(fmaxf(carry.w, r1.w), r2.w));
+      *reinterpret_cast<float4*>(py) = m;
+      py += ystep;
+      carry = r2;
+    }
   }
 }
 
@@ -284,6 +334,14 @@ int launch_maxpool(const PoolArgs& a, cudaStream_t st) {
   const bool small = out_pixels * a.C < (1ll << 31) && (long long)a.N * a.H * a.W < (1ll << 31);
   const long long work = out_pixels * (vec ? a.C / 4 : a.C);
   const int grid = grid_for(work, kThreads, 32);
+  static const int no_strip = [] { const char* e = getenv("B200_POOL_NO_STRIP"); return e ? atoi(e) : 0; }();   // A/B timing only
+  if (!no_strip && vec && small && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2) {
+    const int strips = (a.Ho + kPoolStrip - 1) / kPoolStrip;
+    const long long threads = (long long)a.N * strips * a.Wo * (a.C / 4);
+    maxpool3x3s2_kernel<<<grid_for(threads, kThreads, 32), kThreads, 0, st>>>(a, strips);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (vec && small) maxpool_kernel<true, unsigned><<<grid, kThreads, 0, st>>>(a);
   else if (vec) maxpool_kernel<true, long long><<<grid, kThreads, 0, st>>>(a);
   else if (small) maxpool_kernel<false, unsigned><<<grid, kThreads, 0, st>>>(a);

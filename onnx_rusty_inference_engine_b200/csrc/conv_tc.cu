@@ -17,8 +17,8 @@
 //     puts float 4c+e of a 16-float group in TMEM column 2c+e (e < 2) or 8+2c+e-2 (e >= 2), so the weight
 //     preparation applies the same permutation to K inside every group of 16 (a contraction does not care).
 //   TMEM columns (512): [accumulator stages: {main | correction} x BN each][A stages: {hi 32 | lo 32} each].
-//     BN <= 96: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1);
-//     BN  > 96: one accumulator stage, four A stages; the epilogue drains TMEM to a shared-memory slab first and
+//     BN <= 64: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1) + four A stages;
+//     BN  > 64: one accumulator stage, four A stages; the epilogue drains TMEM to a shared-memory slab first and
 //     releases the accumulator before it touches global memory.
 // One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 20 warps:
 //   warps 0-7   epilogue: warps w, w+4 share TMEM lanes 32*(w%4).. and take the two halves of the tile's channels.
@@ -754,8 +754,11 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.total_tiles = (int)tiles;
   // tensor memory: accumulator stages {main | correction} x BN, then A stages of 64 columns
   static const int force_nacc = [] { const char* e = getenv("B200_TC_NACC"); return e ? atoi(e) : 0; }();   // experiments only
-  p.nacc = (4 * p.BN + 2 * A_STAGE_COLS <= 512) ? 2 : 1;
-  if (force_nacc == 1) p.nacc = 1;
+  // two accumulator stages only when four A stages still fit beside them (BN <= 64): measured on BN = 96 (conv1,
+  // fire6/7 expand3x3), four A stages + one accumulator stage beat two + two by 11-15 %
+  p.nacc = (4 * p.BN + MAX_A_STAGES * A_STAGE_COLS <= 512) ? 2 : 1;
+  if (force_nacc == 1 || force_nacc == 2) p.nacc = force_nacc;
+  if (4 * p.BN + 2 * A_STAGE_COLS > 512) p.nacc = 1;
   p.SA = (512 - p.nacc * 2 * p.BN) / A_STAGE_COLS;
   if (p.SA > MAX_A_STAGES) p.SA = MAX_A_STAGES;
   p.SA &= ~1;   // the two producer sets alternate k-blocks: even stage counts keep a set on its own stages

@@ -114,6 +114,8 @@ POOL_CASES = [
     (1, 64, 12, 12, (3, 3), (2, 2), PAD_VALID, (0, 0, 1, 1)),   # quirk: pads ignored without NOTSET (max_pool_op.rs:88)
     (1, 3, 9, 10, (2, 3), (1, 2), PAD_NOTSET, (1, 2, 0, 1)),    # odd C, asymmetric pads
     (1, 5, 7, 7, (3, 3), (2, 2), PAD_SAME_UPPER, (0, 0, 0, 0)),
+    (2, 8, 33, 31, (3, 3), (2, 2), PAD_NOTSET, (1, 1, 1, 1)),   # strip kernel: two strips of output rows, all four pads
+    (1, 12, 61, 9, (3, 3), (2, 2), PAD_VALID, (0, 0, 0, 0)),    # strip kernel: three strips, ragged last strip
 ]
 
 
