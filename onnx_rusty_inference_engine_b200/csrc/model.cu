@@ -89,6 +89,7 @@ struct b200_model {
   std::map<int64_t, std::unique_ptr<Plan>> plans;
   int opt_cuda_graph = 1;
   int opt_conv_path = 0;
+  int opt_fire_fusion = 1;   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
   int opt_verbose = 0;
   float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
   float* stage_out = nullptr; size_t stage_out_bytes = 0;
@@ -394,12 +395,108 @@ int Planner::do_conv(size_t i) {
   if (const WireNode* c = sole_consumer(out_name, &j)) {
     if (c->op_type == "Relu" && !consumed.count(j)) { relu = 1; consumed.insert(j); out_name = c->output[0]; label += "+Relu"; }
   }
+  int Ceff = C;
+  if (C % 4 != 0 && C >= 3 && x->pad_zeroed && x->v.ld == round_up4(C)) Ceff = round_up4(C);
+  // ---- Fire-module fusion: this 1x1 expand and its 3x3 (pad 1) sibling read the same squeeze output and write
+  // adjacent channel slices of one Concat result.  When both fit one channel tile (M1 + M3 <= 128) they run as ONE
+  // 3x3 convolution whose first M1 filters are the 1x1 weights at the centre tap and exact zeros elsewhere: the
+  // tcgen05 kernel pays per MMA instruction, not per channel, below 128 channels, so the 1x1 branch rides along for
+  // ~8 % of the 3x3 branch's time instead of a launch of its own.  Adding 0 * x terms is exact for finite x.
+  if (m->opt_fire_fusion && m->opt_conv_path != 1 && !chan_add && KH == 1 && KW == 1 && p.strides[0] == 1 && p.strides[1] == 1 &&
+      g.pt == 0 && g.pl == 0 && g.Ho == (int)x->dims[2] && g.Wo == (int)x->dims[3] && Ceff % 4 == 0) {
+    auto r1 = redirect.find(out_name);
+    if (r1 != redirect.end() && r1->second.second == 0) {
+      for (size_t j3 = i + 1; j3 < m->wm.nodes.size(); ++j3) {
+        const WireNode& n3 = m->wm.nodes[j3];
+        if (consumed.count(j3) || n3.op_type != "Conv" || n3.input.size() < 2 || n3.output.empty() || n3.input[0] != n.input[0]) continue;
+        const WireTensor* w3 = m->wm.find_initializer(n3.input[1]);
+        if (!w3) break;
+        auto wd3 = init_dims(m->wm, *w3);
+        if (wd3.size() != 4 || wd3[1] != C || wd3[2] != 3 || wd3[3] != 3 || M + wd3[0] > 128) break;
+        const int M3 = (int)wd3[0];
+        b200_conv_params p3;
+        if (parse_conv_attrs(n3, &p3) || p3.strides[0] != 1 || p3.strides[1] != 1) break;
+        Geo g3;
+        {
+          int ap = p3.auto_pad;
+          if (p3.pads[0] > 0 || p3.pads[1] > 0 || p3.pads[2] > 0 || p3.pads[3] > 0) ap = B200_PAD_NOTSET;
+          if (ref_geometry(ap, (int)x->dims[2], (int)x->dims[3], 3, 3, 1, 1, p3.pads, &g3)) break;
+        }
+        if (g3.pt != 1 || g3.pl != 1 || g3.Ho != g.Ho || g3.Wo != g.Wo) break;
+        const WireTensor* bias3 = nullptr;
+        if (n3.input.size() > 2 && !(bias3 = m->wm.find_initializer(n3.input[2]))) break;
+        // the sibling's tail must match: [Relu] with the same flag, no folded Add, then the Concat's second slot
+        std::string out3 = n3.output[0];
+        size_t jr = 0;
+        bool relu3 = false;
+        if (const WireNode* c = sole_consumer(out3, &jr)) {
+          if (c->op_type == "Add") break;
+          if (c->op_type == "Relu" && !consumed.count(jr)) { relu3 = true; out3 = c->output[0]; }
+        }
+        if ((relu3 ? 1 : 0) != relu) break;
+        auto r3 = redirect.find(out3);
+        if (r3 == redirect.end() || r3->second.first != r1->second.first || r3->second.second != M) break;
+        if ((int64_t)w->init->f32.size() != (int64_t)M * C || (int64_t)w3->f32.size() != (int64_t)M3 * C * 9) break;
+        // ---- committed: one 3x3 convolution with M + M3 filters
+        const int Mt = M + M3;
+        std::string key = "convw:fire:" + w->init->name + "+" + w3->name + ":" + std::to_string(Ceff);
+        float *dwf = nullptr, *dbf = nullptr;
+        if (m->consts.count(key)) dwf = m->consts[key]->p;
+        else {
+          std::vector<float> h((size_t)Mt * 9 * Ceff, 0.f);
+          for (int mm = 0; mm < M; ++mm)
+            for (int c = 0; c < C; ++c) h[(((size_t)mm * 3 + 1) * 3 + 1) * Ceff + c] = w->init->f32[(size_t)mm * C + c];
+          for (int mm = 0; mm < M3; ++mm)
+            for (int c = 0; c < C; ++c)
+              for (int r = 0; r < 3; ++r)
+                for (int sx = 0; sx < 3; ++sx)
+                  h[(((size_t)(M + mm) * 3 + r) * 3 + sx) * Ceff + c] = w3->f32[(((size_t)mm * C + c) * 3 + r) * 3 + sx];
+          B200_TRY(upload_const(m, key, h, &dwf));
+        }
+        if (bias || bias3) {
+          if ((bias && bias->f32.size() != (size_t)M) || (bias3 && bias3->f32.size() != (size_t)M3)) B200_FAIL(B200_EINVAL, "Conv %s: bias length", n.name.c_str());
+          std::vector<float> hb((size_t)Mt, 0.f);
+          if (bias) std::copy(bias->f32.begin(), bias->f32.end(), hb.begin());
+          if (bias3) std::copy(bias3->f32.begin(), bias3->f32.end(), hb.begin() + M);
+          B200_TRY(upload_const(m, "vec:fire:" + (bias ? bias->name : std::string("-")) + "+" + (bias3 ? bias3->name : std::string("-")), hb, &dbf));
+        }
+        ConvArgs a{};
+        a.x = x->v.p; a.N = x->v.N; a.C = Ceff; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
+        a.w = dwf; a.M = Mt; a.KH = 3; a.KW = 3; a.K = 9 * Ceff; a.wc = Ceff; a.ldw = a.K;
+        a.bias = dbf; a.chan_add = nullptr;
+        a.Ho = g.Ho; a.Wo = g.Wo; a.sh = 1; a.sw = 1; a.pt = 1; a.pl = 1; a.relu = relu;
+        if (tc_supported(a) != 0) break;
+        Val y1, y3;
+        y1.rank = 4; memcpy(y1.dims, yd, sizeof(yd));
+        y3 = y1; y3.dims[1] = M3;
+        B200_TRY(place(out_name, &y1));
+        B200_TRY(place(out3, &y3));
+        a.y = y1.v.p; a.ldy = y1.v.ld;
+        consumed.insert(j3);
+        if (relu3) consumed.insert(jr);
+        const double P = (double)y1.v.pixels();
+        const double flops = 2.0 * P * C * ((double)M + 9.0 * M3);
+        const double bytes = 4.0 * ((double)x->v.pixels() * C + P * Mt + (double)C * (M + 9.0 * M3));
+        std::shared_ptr<TcWeights> tcw;
+        if (!dry) {
+          auto it = m->tc_weights.find("tc:" + key);
+          if (it == m->tc_weights.end()) {
+            B200_TRY(tc_prepare_weights(dwf, Mt, a.K, m->ctx->stream, &tcw));
+            m->tc_weights["tc:" + key] = tcw;
+          } else tcw = it->second;
+        }
+        std::string l3 = n3.name.empty() ? n3.output[0] : n3.name;
+        add_step(label + " | " + l3 + (relu3 ? "+Relu" : ""), "conv_tc", flops, bytes, [a, tcw](cudaStream_t st) { return launch_conv_tc(a, *tcw, st); });
+        env[out_name] = y1;
+        env[out3] = y3;
+        return 0;
+      }
+    }
+  }
   Val y;
   y.rank = 4; memcpy(y.dims, yd, sizeof(yd));
   B200_TRY(place(out_name, &y));
   // ---- operand preparation
-  int Ceff = C;
-  if (C % 4 != 0 && C >= 3 && x->pad_zeroed && x->v.ld == round_up4(C)) Ceff = round_up4(C);
   float *dw = nullptr, *db = nullptr, *dadd = nullptr;
   B200_TRY(conv_weights(*w->init, {M, C, KH, KW}, Ceff, &dw));
   if (bias) B200_TRY(vec_const(*bias, (size_t)M, &db));
@@ -949,6 +1046,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
     if (value < 0 || value > 2) B200_FAIL(B200_EINVAL, "conv_path must be 0, 1 or 2");
     if (m->opt_conv_path != (int)value) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_conv_path = (int)value;
+  } else if (k == "fire_fusion") {
+    if (m->opt_fire_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_fire_fusion = value ? 1 : 0;
   } else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
   else B200_FAIL(B200_EINVAL, "unknown option %s", key);
   return 0;

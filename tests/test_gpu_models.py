@@ -90,6 +90,25 @@ def test_squeezenet_synth_vs_oracle(ctx, synth_onnx):
     assert_close(got_simt, want, "squeezenet synth (conv_path=1)")
 
 
+def test_fire_fusion_matches_separate_launches(ctx, synth_onnx):
+    """fire2 / fire3: expand1x1 + expand3x3 as one convolution (1x1 filters at the centre tap, exact zeros elsewhere)
+    must give what the two separate launches give, and both must match the oracle."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(3, seed=7)
+    eng = Engine(synth_onnx, ctx=ctx)
+    fused = eng(xs)
+    n_fused = eng.model.launches_per_run(3)
+    eng.model.set_option("fire_fusion", 0)
+    separate = eng(xs)
+    n_sep = eng.model.launches_per_run(3)
+    assert n_sep == n_fused + 2, (n_sep, n_fused)          # fire2 and fire3 (M1 + M3 = 128) fuse; fire4.. do not
+    assert_close(fused, separate, "fire fusion vs separate launches")
+    want = rm.run_batch(ow.load_model(synth_onnx), xs[:2], threads=2)
+    assert_close(fused[:2], want, "fire fusion vs oracle")
+
+
 def test_squeezenet_batch_properties(ctx, synth_onnx):
     """Config 3 at full size (batch 256): batch-position invariance and softmax normalisation."""
     from onnx_rusty_inference_engine_b200 import synth
