@@ -562,27 +562,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         tmem_ld_wait();
         const uint32_t boff = 4u * (uint32_t)(m0 + g * 16);
         const uint32_t crow = my_row + ((uint32_t)(g - g_begin) << 6);
+        // the shared-memory accesses are volatile asm (kept in program order), so batch them: four bias loads, the
+        // arithmetic, four slab stores -- one load latency per group instead of four
+        float4 b4[4], c4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 b4, c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(sbias + boff + 16u * q));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4[q].x), "=f"(b4[q].y), "=f"(b4[q].z), "=f"(b4[q].w) : "r"(sbias + boff + 16u * q));
           if (HAS_ADD)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(sadd + boff + 16u * q));
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-          float o[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4[q].x), "=f"(c4[q].y), "=f"(c4[q].z), "=f"(c4[q].w) : "r"(sadd + boff + 16u * q));
+        }
+        float o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float bb[4] = {b4[q].x, b4[q].y, b4[q].z, b4[q].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = q * 4 + e;
             float val = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
             val = val + bb[e];                     // add_bias, convolution_op.rs:705 (0 when the node has no bias)
-            if (HAS_ADD) val = val + cc[e];        // folded Add node, add_op.rs:75 (a second rounding, as upstream)
+            if (HAS_ADD) {                         // folded Add node, add_op.rs:75 (a second rounding, as upstream)
+              const float cc[4] = {c4[q].x, c4[q].y, c4[q].z, c4[q].w};
+              val = val + cc[e];
+            }
             if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
-            o[e] = val;
+            o[j] = val;
           }
-          // 16-byte chunk (g - g_begin) * 4 + q of the slab row, XOR-swizzled by the row
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((crow + 16u * q) ^ lane_sw), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
         }
+        // 16-byte chunk (g - g_begin) * 4 + q of the slab row, XOR-swizzled by the row
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((crow + 16u * q) ^ lane_sw), "f"(o[4 * q]), "f"(o[4 * q + 1]), "f"(o[4 * q + 2]), "f"(o[4 * q + 3]) : "memory");
       }
       // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp before storing
       tc_fence_before();
@@ -608,14 +617,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           const long long dstep = (long long)step * a.ldy;
           uint32_t src = slab + (uint32_t)(rr * p.slab_pitch) + ((uint32_t)c << 4);
           const uint32_t sstep = (uint32_t)(step * p.slab_pitch);
-#pragma unroll 4
-          for (int it = 0; it < (1 << lw); ++it) {
-            if (rr < rows_ok) {
-              float4 val;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(src ^ ((uint32_t)(rr & 7) << 4)));
-              *reinterpret_cast<float4*>(dst) = val;
-            }
-            rr += step; dst += dstep; src += sstep;
+          // two rows per round: both loads, then both stores (the asm loads keep program order)
+          for (int it = 0; it < (1 << lw); it += 2) {
+            float4 v0, v1;
+            const bool ok0 = rr < rows_ok, ok1 = rr + step < rows_ok;
+            if (ok0) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src ^ ((uint32_t)(rr & 7) << 4)));
+            if (ok1) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"((src + sstep) ^ ((uint32_t)((rr + step) & 7) << 4)));
+            if (ok0) *reinterpret_cast<float4*>(dst) = v0;
+            if (ok1) *reinterpret_cast<float4*>(dst + dstep) = v1;
+            rr += 2 * step; dst += 2 * dstep; src += 2 * sstep;
           }
           cdone += w;
         }
