@@ -234,7 +234,10 @@ def run_own(args):
         peaks = measured_peaks()
         # ---- roofline of the dominant kernel family (Conv), timed per launch with CUDA events on the launching
         # stream inside the library (b200_model_profile), L2 flushed before every timed launch
-        prof = eng.model.profile(B, iters=3, flush_l2=True)
+        # ("in_order": the launch list runs in model order and every launch is timed in place, so it sees the cache
+        # state it sees inside a timed step -- its input was just written by its predecessor; a step's activations
+        # exceed the L2.  profiles/ also holds the cold-cache variant, flush_l2=True.)
+        prof = eng.model.profile(B, iters=5, flush_l2="in_order")
         conv = [p for p in prof if p["kind"].startswith("conv")]
         conv_ms = sum(p["ms"] for p in conv)
         conv_flops = sum(p["flops"] for p in conv)
@@ -245,18 +248,21 @@ def run_own(args):
         bw = [p for p in prof if not p["kind"].startswith("conv") and not p["kind"].startswith("matmul")]
         bw_ms = sum(p["ms"] for p in bw)
         bw_gbs = sum(p["bytes"] for p in bw) / (bw_ms * 1e-3) / 1e9 if bw_ms > 0 else None
-        # DRAM bytes of the same 26 launches from the committed ncu pass (profiles/README.md); null if absent
+        # DRAM bytes of the same launches from the committed ncu pass (profiles/README.md); null if absent
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1_tc_step_dram_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r1b_step_dram_traffic.json")
         if os.path.exists(tp) and B == 256 and not args.conv_path:
             with open(tp) as f:
-                traffic = json.load(f).get("conv_tc_dram_bytes_per_step")
-            traffic_src = "profiles/r1_tc_step_dram_traffic.json (ncu dram__bytes_read+write.sum, 26 conv launches of one step)"
+                tj = json.load(f)
+            if tj.get("conv_tc_launches") == len(conv):
+                traffic = tj.get("conv_tc_dram_bytes_per_step")
+                traffic_src = (f"profiles/r1b_step_dram_traffic.json (ncu dram__bytes_read+write.sum, the {len(conv)} conv "
+                               "launches of one step)")
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
-            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": "step: the 26 conv launches (one kernel, conv_tc_kernel)",
-            "kernel": "conv (all 26 Conv launches of one step: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
+            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel), per-launch CUDA events in model order",
+            "kernel": f"conv (all {len(conv)} Conv launches of one step, 26 Conv nodes: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
             "peak_source": f"{peaks['src']}: bf16_tflops_sustained {peaks['bf16_tflops_sustained']} / 2 (TF32) / 3 (3xTF32)",
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / total_ms if total_ms else None,
             "top_launch": {"name": top["name"], "kind": top["kind"], "ms": top["ms"],

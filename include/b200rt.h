@@ -161,11 +161,13 @@ int b200_model_sync(b200_model *m);
  * on the context's device; asynchronous on the context's stream. */
 int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float *d_out);
 /* Options: "cuda_graph" (0/1, default 1), "conv_path" (0 = auto, 1 = force CUDA-core fp32 cross-check
- * kernel, 2 = force tcgen05 3xTF32), "verbose" (0/1: print the reference's per-node lines). */
+ * kernel, 2 = force tcgen05 3xTF32), "fire_fusion" (0/1, default 1: expand1x1 + expand3x3 of a Fire module as one
+ * launch when both fit one channel tile), "verbose" (0/1: print the reference's per-node lines). */
 int b200_model_set_option(b200_model *m, const char *key, int64_t value);
 /* Per-launch profile of the last planned batch size: runs each planned launch `iters` times between CUDA
- * events (L2 flushed before every timed launch when flush_l2 != 0) and writes one JSON document
- * into buf: [{"name":..,"kind":..,"ms":..,"flops":..,"bytes":..}, ...]. */
+ * events and writes one JSON document into buf.  flush_l2: 0 = repeat each launch back to back, 1 = flush the L2
+ * before every timed launch (cold cache), 2 = run the whole launch list in model order `iters` times and time every
+ * launch in place (the cache state of a real run).  Format: [{"name":..,"kind":..,"ms":..,"flops":..,"bytes":..}, ...]. */
 int b200_model_profile(b200_model *m, int64_t batch, int iters, int flush_l2, char *buf, size_t cap);
 /* Number of kernel launches one b200_model_run_device of `batch` images issues. */
 int64_t b200_model_launches_per_run(b200_model *m, int64_t batch);

@@ -328,7 +328,9 @@ class Model:
     def profile(self, batch: int, iters: int = 5, flush_l2: bool = True):
         import json
         buf = C.create_string_buffer(1 << 20)
-        check(lib().b200_model_profile(self._h, int(batch), int(iters), 1 if flush_l2 else 0, buf, len(buf)))
+        # flush_l2: False / True, or "in_order" (2): the launch list runs in model order, each launch timed in place
+        mode = 2 if flush_l2 == "in_order" else (1 if flush_l2 else 0)
+        check(lib().b200_model_profile(self._h, int(batch), int(iters), mode, buf, len(buf)))
         return json.loads(buf.value.decode())
 
     def close(self) -> None:

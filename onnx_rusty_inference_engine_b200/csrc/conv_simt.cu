@@ -9,6 +9,8 @@
 // GEMM view: D[P x M] = A[P x K] * B[M x K]^T with P = N*Ho*Wo pixels, K = KH*KW*C ordered (r, s, c) so that
 // both A (an input pixel's channels) and B (a weight row) are contiguous along K.
 // Tile: 128 pixels x BN channels per 256-thread CTA, BK = 16, register tile 8 x TN, register-staged prefetch.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace b200 {
@@ -219,9 +221,96 @@ int launch_bn(const ConvArgs& a, bool vec, cudaStream_t st) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Direct convolution for few output channels and a short reduction (MNIST's first layer: C = 1, 5x5, M = 8).
+// The implicit-GEMM tile above wastes most of a 128 x 16 tile there and the layer is bandwidth-class work
+// (1.6 KFLOP and 6.3 KB of traffic per image row): one thread per output pixel keeps all MT accumulators in
+// registers, walks k = (r, s, c) in the same order as the GEMM kernels, reads its input taps coalesced across
+// the warp (consecutive output columns) and the weights as broadcast 128-bit shared-memory loads.
+template <int MT>
+__global__ void __launch_bounds__(256) conv_direct_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) float wsm[];   // [K][MT], zero padded to MT filters
+  for (int i = threadIdx.x; i < a.K * MT; i += blockDim.x) {
+    const int k = i / MT, m = i - k * MT;
+    const int tap = k / a.C, c = k - tap * a.C;
+    wsm[i] = (m < a.M) ? __ldg(a.w + (long long)m * a.ldw + (long long)tap * a.wc + c) : 0.f;
+  }
+  __syncthreads();
+  const long long P = (long long)a.N * a.Ho * a.Wo;
+  const bool vec_out = (a.M % 4 == 0) && (a.ldy % 4 == 0) && ((((uintptr_t)a.y) & 15) == 0);
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(p % a.Wo);
+    const long long t = p / a.Wo;
+    const int ho = (int)(t % a.Ho);
+    const long long n = t / a.Ho;
+    const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
+    const float* img = a.x + n * (long long)a.H * a.W * a.ldx;
+    float acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+    const float4* wrow = reinterpret_cast<const float4*>(wsm);
+    for (int r = 0; r < a.KH; ++r) {
+      const int h = h0 + r;
+      const bool hin = (unsigned)h < (unsigned)a.H;
+      for (int sx = 0; sx < a.KW; ++sx) {
+        const int w = w0 + sx;
+        const bool in = hin && (unsigned)w < (unsigned)a.W;
+        const float* px = img + ((long long)h * a.W + w) * a.ldx;
+        for (int c = 0; c < a.C; ++c) {
+          const float x = in ? __ldg(px + c) : 0.f;   // zero padding, convolution_op.rs:560-663
+#pragma unroll
+          for (int q = 0; q < MT / 4; ++q) {
+            const float4 w4 = wrow[q];
+            acc[4 * q + 0] = fmaf(x, w4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x, w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x, w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x, w4.w, acc[4 * q + 3]);
+          }
+          wrow += MT / 4;
+        }
+      }
+    }
+    float* py = a.y + p * a.ldy;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < a.M) {
+        float v = acc[m];
+        if (a.bias) v += __ldg(a.bias + m);          // add_bias, convolution_op.rs:705
+        if (a.chan_add) v += __ldg(a.chan_add + m);  // folded Add, add_op.rs:75
+        if (a.relu) v = fmaxf(v, 0.f);               // relu_op.rs:31-33
+        acc[m] = v;
+      }
+    }
+    if (vec_out) {
+#pragma unroll
+      for (int q = 0; q < MT / 4; ++q)
+        if (4 * q < a.M) *reinterpret_cast<float4*>(py + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        if (m < a.M) py[m] = acc[m];
+    }
+  }
+}
+
+static bool direct_eligible(const ConvArgs& a) {
+  static const int off = [] { const char* e = getenv("B200_NO_DIRECT_CONV"); return e ? atoi(e) : 0; }();   // A/B timing only
+  return !off && a.M <= 16 && a.K <= 128 && a.C <= 4;
+}
+
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
   const long long P = (long long)a.N * a.Ho * a.Wo;
   if (P == 0 || a.M == 0) return 0;
+  if (direct_eligible(a)) {
+    const int MT = a.M <= 8 ? 8 : 16;
+    long long blocks = (P + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const size_t smem = (size_t)a.K * MT * sizeof(float);
+    if (MT == 8) conv_direct_kernel<8><<<(int)blocks, 256, smem, st>>>(a);
+    else conv_direct_kernel<16><<<(int)blocks, 256, smem, st>>>(a);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
   const bool vec = a.C % 4 == 0 && a.wc == a.C && a.ldx % 4 == 0 && a.ldw % 4 == 0 && (((uintptr_t)a.x) & 15) == 0 &&
                    (((uintptr_t)a.w) & 15) == 0;
   if (a.M <= 16) return launch_bn<16>(a, vec, st);

@@ -1174,6 +1174,28 @@ int b200_model_profile(b200_model* m, int64_t batch, int iters, int flush_l2, ch
   js << "[";
   // the input transform is part of every run: profile it as step 0 (reads its own output buffer as source shape only)
   int rc = 0;
+  if (flush_l2 == 2) {
+    // in-order mode: the whole launch list runs `iters` times in model order and every launch is timed where it
+    // stands, so it sees the cache state it sees in a real run (its input was just written by its predecessor)
+    std::vector<double> acc(p->steps.size(), 0.0);
+    for (int it = -1; it < iters && rc == 0; ++it) {   // it == -1: warm pass
+      for (size_t i = 0; i < p->steps.size() && rc == 0; ++i) {
+        cudaEventRecord(e0, st);
+        rc = p->steps[i].run(st);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { rc = B200_ECUDA; set_error("profile: step %s failed: %s", p->steps[i].name.c_str(), cudaGetErrorString(cudaGetLastError())); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it >= 0) acc[i] += ms;
+      }
+    }
+    for (size_t i = 0; i < p->steps.size() && rc == 0; ++i) {
+      Step& s = p->steps[i];
+      if (i) js << ",";
+      js << "{\"name\":\"" << s.name << "\",\"kind\":\"" << s.kind << "\",\"ms\":" << (acc[i] / iters) << ",\"flops\":" << s.flops
+         << ",\"bytes\":" << s.bytes << "}";
+    }
+  } else
   for (size_t i = 0; i < p->steps.size() && rc == 0; ++i) {
     Step& s = p->steps[i];
     double total_ms = 0;

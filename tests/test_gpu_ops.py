@@ -34,6 +34,8 @@ CONV_CASES = [
     (1, 4, 10, 10, 6, 3, 3, (2, 2), PAD_SAME_UPPER, (0, 0, 0, 0), False),   # SAME with odd total pad (swapped split)
     (1, 2, 8, 7, 3, 4, 4, (1, 1), PAD_SAME_LOWER, (0, 0, 0, 0), True),      # SAME_LOWER, even kernel -> odd pad
     (1, 1, 5, 6, 1, 5, 2, (1, 1), PAD_VALID, (0, 0, 0, 0), False),          # convolution_op.rs:728 fixture shape
+    (2, 3, 20, 17, 16, 3, 3, (2, 2), PAD_VALID, (1, 1, 1, 1), True),        # direct kernel, 16 filters, all four pads
+    (3, 2, 9, 33, 12, 2, 5, (1, 2), PAD_VALID, (0, 2, 1, 2), True),         # direct kernel, M = 12 of 16 lanes used
 ]
 
 

@@ -13,7 +13,7 @@ stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Is
 data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
 tot_s = sum(int(r[iS]) for r in data); tot_i = sum(int(r[iI]) for r in data)
 print("total samples", tot_s, "total warp-inst", tot_i)
-marks = ('UTCHMMA', 'UTMALDG', 'LDTM', 'LDG.E', 'STS.128', 'STG.E', 'UTCBAR', 'BAR.SYNC', 'SYNCS.ARRIVE', 'LDS.128', 'EXIT',
+marks = ('UTCHMMA', 'UTMALDG', 'LDTM', 'STTM', 'LDG.E', 'STS.128', 'STG.E', 'UTCBAR', 'BAR.SYNC', 'SYNCS.ARRIVE', 'LDS.128', 'EXIT',
          'SYNCS.PHASECHK', 'FENCE', 'MEMBAR')
 seg_s = seg_i = 0
 agg = [0] * len(stall_cols)
