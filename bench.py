@@ -167,6 +167,9 @@ def run_own(args):
     eng = Engine(SYNTH_MODEL, device=local, stream=stream.cuda_stream)
     if args.conv_path:
         eng.model.set_option("conv_path", args.conv_path)
+    for kv in args.model_opt:            # A/B experiments: --model-opt alt_order=0 --model-opt fire_fusion=0
+        k, v = kv.split("=")
+        eng.model.set_option(k, int(v))
 
     # synthetic inputs: two distinct resident batches per rank (each 154 MB > the 126 MB L2, and a step streams
     # gigabytes of activations, so no input or activation survives in L2 between timed steps)
@@ -312,6 +315,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--conv-path", type=int, default=0, dest="conv_path")
     ap.add_argument("--profile-out", default=None, dest="profile_out")
+    ap.add_argument("--model-opt", action="append", default=[], dest="model_opt")
     ap.add_argument("--no-cpu-baseline", action="store_true", dest="no_cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":

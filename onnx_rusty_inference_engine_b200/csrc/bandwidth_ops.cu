@@ -126,7 +126,8 @@ constexpr int kPoolStrip = 14;   // output rows per thread
 __global__ void maxpool3x3s2_kernel(PoolArgs a, int strips) {
   const int CV = a.C / 4;
   const unsigned total = (unsigned)a.N * strips * a.Wo * CV;   // < 2^31, checked by the launcher
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+    const unsigned i = a.reverse ? total - 1u - j : j;
     const int c = (int)(i % CV);
     unsigned t = i / CV;
     const int wo = (int)(t % a.Wo);

@@ -77,6 +77,7 @@ struct TcParams {
   int nacc;        // accumulator stages (tensor memory): 2 when 4*BN + 2*64 <= 512, else 1
   int nkb;         // k-blocks per tile
   int n_tiles_n;   // channel tiles
+  int reverse;     // walk the tiles from the last to the first (see ConvArgs::reverse)
   int total_tiles; // pixel tiles x channel tiles
   int Mpad;        // weight rows per half (hi / lo)
   int P;           // output pixels (fits in int32, checked on the host)
@@ -371,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       auto set_tile = [&](int tile) {
         // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
         // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
-        const int p0 = (tile / p.n_tiles_n) * BM;
+        const int p0 = ((p.reverse ? p.total_tiles - 1 - tile : tile) / p.n_tiles_n) * BM;
         const int t0 = p0 / a.Wo, wo0 = p0 - t0 * a.Wo;
         const int n0 = t0 / a.Ho, ho0 = t0 - n0 * a.Ho;
         hmask = 0; wmask = 0;
@@ -444,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int m0 = (t % p.n_tiles_n) * p.BN;
+        const int m0 = ((p.reverse ? p.total_tiles - 1 - t : t) % p.n_tiles_n) * p.BN;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(empty_b(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
@@ -462,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       int r = 0;
       uint32_t rph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int p0 = (t / p.n_tiles_n) * BM;
+        const int p0 = ((p.reverse ? p.total_tiles - 1 - t : t) / p.n_tiles_n) * BM;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(raw_empty(r), rph ^ 1u);
           mbar_expect_tx(raw_full(r), (uint32_t)A_TILE_BYTES);
@@ -550,8 +551,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
       const int as = p.nacc == 2 ? (tc & 1) : 0;
       const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
-      const int p0 = (t / p.n_tiles_n) * BM;
-      const int m0 = (t % p.n_tiles_n) * p.BN;
+      const int tt = p.reverse ? p.total_tiles - 1 - t : t;
+      const int p0 = (tt / p.n_tiles_n) * BM;
+      const int m0 = (tt % p.n_tiles_n) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * p.BN);
@@ -759,6 +761,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.nkb = w.Kpad / BK;
   p.P = (int)P;
   p.n_tiles_n = w.Mpad / w.BN;
+  p.reverse = a.reverse ? 1 : 0;
   const long long tiles = ((P + BM - 1) / BM) * p.n_tiles_n;
   if (tiles >= (1ll << 31)) B200_FAIL(B200_EUNSUPPORTED, "too many tiles");
   p.total_tiles = (int)tiles;

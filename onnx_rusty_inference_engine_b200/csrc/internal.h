@@ -60,12 +60,17 @@ struct ConvArgs {
   float* y; int Ho, Wo, ldy;
   int sh, sw, pt, pl;                         // strides, top/left zero padding
   int relu;
+  // Walk the output tiles from the last to the first.  The graph executor alternates the direction from launch to
+  // launch: a launch then starts on the part of its input that its predecessor wrote last and that is still in the
+  // 126 MB L2.  Results do not depend on it (tiles are independent).
+  int reverse;
 };
 
 struct PoolArgs {
   const float* x; int N, C, H, W, ldx;
   float* y; int Ho, Wo, ldy;
   int kh, kw, sh, sw, pt, pl;                 // zero-fill padding (reference semantics)
+  int reverse;                                // as ConvArgs::reverse (strip kernel only)
 };
 
 // ---------------------------------------------------------------- kernel launchers (all async on `st`)

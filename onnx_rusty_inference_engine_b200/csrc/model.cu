@@ -89,7 +89,8 @@ struct b200_model {
   std::map<int64_t, std::unique_ptr<Plan>> plans;
   int opt_cuda_graph = 1;
   int opt_conv_path = 0;
-  int opt_fire_fusion = 1;   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
+  int opt_fire_fusion = 1;
+  int opt_alt_order = 1;     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
   int opt_verbose = 0;
   float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
   float* stage_out = nullptr; size_t stage_out_bytes = 0;
@@ -228,7 +229,13 @@ struct Planner {
     return 0;
   }
 
+  // Launches alternate their walking direction (ConvArgs::reverse): launch k starts on what launch k-1 wrote last,
+  // which is still in L2.  The Fire pattern keeps the alternation meaningful: squeeze F, expand R (, expand F), next
+  // squeeze the opposite of the last expand.
+  size_t step_counter = 0;
+  int next_reverse() const { return m->opt_alt_order ? (int)(step_counter & 1) : 0; }
   void add_step(const std::string& name, const char* kind, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
+    ++step_counter;
     if (dry) return;
     Step s; s.name = name; s.kind = kind; s.flops = flops; s.bytes = bytes; s.run = std::move(fn);
     plan->steps.push_back(std::move(s));
@@ -465,6 +472,7 @@ int Planner::do_conv(size_t i) {
         a.w = dwf; a.M = Mt; a.KH = 3; a.KW = 3; a.K = 9 * Ceff; a.wc = Ceff; a.ldw = a.K;
         a.bias = dbf; a.chan_add = nullptr;
         a.Ho = g.Ho; a.Wo = g.Wo; a.sh = 1; a.sw = 1; a.pt = 1; a.pl = 1; a.relu = relu;
+        a.reverse = next_reverse();
         if (tc_supported(a) != 0) break;
         Val y1, y3;
         y1.rank = 4; memcpy(y1.dims, yd, sizeof(yd));
@@ -507,6 +515,7 @@ int Planner::do_conv(size_t i) {
   a.bias = db; a.chan_add = dadd;
   a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
   a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl; a.relu = relu;
+  a.reverse = next_reverse();
   const double P = (double)y.v.pixels();
   const double flops = 2.0 * P * M * C * KH * KW;
   const double bytes = 4.0 * ((double)x->v.pixels() * C + P * M + (double)M * C * KH * KW);
@@ -547,6 +556,7 @@ int Planner::do_maxpool(size_t i) {
   a.x = x->v.p; a.N = x->v.N; a.C = x->v.C; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
   a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
   a.kh = (int)p.kernel[0]; a.kw = (int)p.kernel[1]; a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl;
+  a.reverse = next_reverse();
   const double bytes = 4.0 * ((double)x->v.numel() + (double)y.v.numel());
   add_step(n.name.empty() ? n.output[0] : n.name, "maxpool", 0, bytes, [a](cudaStream_t st) { return launch_maxpool(a, st); });
   env[n.output[0]] = y;
@@ -795,7 +805,7 @@ int Planner::do_softmax(size_t i) {
 }
 
 int Planner::run() {
-  env.clear(); consumed.clear(); arena_cursor = 0; arena_allocs.clear();
+  env.clear(); consumed.clear(); arena_cursor = 0; arena_allocs.clear(); step_counter = 0;
   n_consumers.clear();
   for (auto& n : m->wm.nodes) for (auto& in : n.input) n_consumers[in]++;
   redirect.clear();
@@ -1049,6 +1059,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
   } else if (k == "fire_fusion") {
     if (m->opt_fire_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_fire_fusion = value ? 1 : 0;
+  } else if (k == "alt_order") {
+    if (m->opt_alt_order != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_alt_order = value ? 1 : 0;
   } else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
   else B200_FAIL(B200_EINVAL, "unknown option %s", key);
   return 0;

@@ -16,8 +16,17 @@ LAYERS = {  # name: (N, C, H, W, M, k, stride, pad)
     "f8_sq": (256, 384, 27, 27, 64, 1, 1, 0),
     "f8_e3": (256, 64, 27, 27, 256, 3, 1, 1),
     "conv10": (256, 512, 13, 13, 1000, 1, 1, 0),
+    "f5_e1": (256, 32, 27, 27, 128, 1, 1, 0),
+    "f6_e1": (256, 48, 27, 27, 192, 1, 1, 0),
+    "f6_e3": (256, 48, 27, 27, 192, 3, 1, 1),
+    "f8_e1": (256, 64, 27, 27, 256, 1, 1, 0),
+    "f9_e1": (256, 64, 13, 13, 256, 1, 1, 0),
+    "f9_e3": (256, 64, 13, 13, 256, 3, 1, 1),
+    "f9_sq": (256, 512, 13, 13, 64, 1, 1, 0),
+    "tiny1": (1, 32, 8, 16, 128, 1, 1, 0),     # one tile, one k-block: the kernel's fixed cost
+    "tiny148": (148, 32, 8, 16, 128, 1, 1, 0),  # one tile per SM
 }
-names = sys.argv[1:] or list(LAYERS)
+names = sys.argv[1:] or [n for n in LAYERS if not n.startswith('tiny')]
 torch.cuda.set_device(0)
 s = torch.cuda.Stream()
 torch.cuda.set_stream(s)
