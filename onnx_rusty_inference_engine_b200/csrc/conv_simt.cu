@@ -293,6 +293,94 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvArgs a) {
   }
 }
 
+// The same with a 4-pixel register tile along the output row (stride-1 columns, KW <= 8): the KW + 3 input values of
+// a kernel row are loaded once and shared by the four pixels (2 loads per pixel and kernel row instead of KW), and
+// every broadcast weight vector feeds 4 x 4 FMAs.
+template <int MT>
+__global__ void __launch_bounds__(256) conv_direct4_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) float wsm[];   // [K][MT], k = (r*KW + s)*C + c, zero padded to MT filters
+  for (int i = threadIdx.x; i < a.K * MT; i += blockDim.x) {
+    const int k = i / MT, m = i - k * MT;
+    const int tap = k / a.C, c = k - tap * a.C;
+    wsm[i] = (m < a.M) ? __ldg(a.w + (long long)m * a.ldw + (long long)tap * a.wc + c) : 0.f;
+  }
+  __syncthreads();
+  const int WQ = (a.Wo + 3) >> 2;
+  const long long G = (long long)a.N * a.Ho * WQ;
+  const bool vec_out = (a.M % 4 == 0) && (a.ldy % 4 == 0) && ((((uintptr_t)a.y) & 15) == 0);
+  const float4* wv = reinterpret_cast<const float4*>(wsm);
+  for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < G; gi += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(gi % WQ);
+    const long long t = gi / WQ;
+    const int ho = (int)(t % a.Ho);
+    const long long n = t / a.Ho;
+    const int wo0 = wq * 4;
+    const int h0 = ho * a.sh - a.pt, w0 = wo0 - a.pl;   // sw == 1
+    const float* img = a.x + n * (long long)a.H * a.W * a.ldx;
+    float acc[4][MT];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int m = 0; m < MT; ++m) acc[q][m] = 0.f;
+    for (int r = 0; r < a.KH; ++r) {
+      const int h = h0 + r;
+      if ((unsigned)h >= (unsigned)a.H) continue;       // a padded row contributes 0 to every tap
+      const float* row = img + (long long)h * a.W * a.ldx;
+      for (int c = 0; c < a.C; ++c) {
+        float x[11];
+#pragma unroll
+        for (int j = 0; j < 11; ++j) {
+          const int w = w0 + j;
+          x[j] = (j < a.KW + 3 && (unsigned)w < (unsigned)a.W) ? __ldg(row + (long long)w * a.ldx + c) : 0.f;
+        }
+#pragma unroll
+        for (int sx = 0; sx < 8; ++sx) {
+          if (sx < a.KW) {
+            const float4* wk = wv + ((r * a.KW + sx) * a.C + c) * (MT / 4);
+#pragma unroll
+            for (int v = 0; v < MT / 4; ++v) {
+              const float4 w4 = wk[v];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                acc[q][4 * v + 0] = fmaf(x[sx + q], w4.x, acc[q][4 * v + 0]);
+                acc[q][4 * v + 1] = fmaf(x[sx + q], w4.y, acc[q][4 * v + 1]);
+                acc[q][4 * v + 2] = fmaf(x[sx + q], w4.z, acc[q][4 * v + 2]);
+                acc[q][4 * v + 3] = fmaf(x[sx + q], w4.w, acc[q][4 * v + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+    const long long p0 = (n * a.Ho + ho) * (long long)a.Wo + wo0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (wo0 + q < a.Wo) {
+        float* py = a.y + (p0 + q) * a.ldy;
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          if (m < a.M) {
+            float v = acc[q][m];
+            if (a.bias) v += __ldg(a.bias + m);          // add_bias, convolution_op.rs:705
+            if (a.chan_add) v += __ldg(a.chan_add + m);  // folded Add, add_op.rs:75
+            if (a.relu) v = fmaxf(v, 0.f);               // relu_op.rs:31-33
+            acc[q][m] = v;
+          }
+        }
+        if (vec_out) {
+#pragma unroll
+          for (int v = 0; v < MT / 4; ++v)
+            if (4 * v < a.M) *reinterpret_cast<float4*>(py + 4 * v) = make_float4(acc[q][4 * v], acc[q][4 * v + 1], acc[q][4 * v + 2], acc[q][4 * v + 3]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < MT; ++m)
+            if (m < a.M) py[m] = acc[q][m];
+        }
+      }
+    }
+  }
+}
+
 static bool direct_eligible(const ConvArgs& a) {
   static const int off = [] { const char* e = getenv("B200_NO_DIRECT_CONV"); return e ? atoi(e) : 0; }();   // A/B timing only
   return !off && a.M <= 16 && a.K <= 128 && a.C <= 4;
@@ -306,7 +394,14 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
     long long blocks = (P + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     const size_t smem = (size_t)a.K * MT * sizeof(float);
-    if (MT == 8) conv_direct_kernel<8><<<(int)blocks, 256, smem, st>>>(a);
+    static const int no4 = [] { const char* e = getenv("B200_NO_DIRECT4"); return e ? atoi(e) : 0; }();   // A/B timing only
+    if (!no4 && a.sw == 1 && a.KW <= 8) {
+      const long long G = (long long)a.N * a.Ho * ((a.Wo + 3) / 4);
+      long long b4 = (G + 255) / 256;
+      if (b4 > 148 * 16) b4 = 148 * 16;
+      if (MT == 8) conv_direct4_kernel<8><<<(int)b4, 256, smem, st>>>(a);
+      else conv_direct4_kernel<16><<<(int)b4, 256, smem, st>>>(a);
+    } else if (MT == 8) conv_direct_kernel<8><<<(int)blocks, 256, smem, st>>>(a);
     else conv_direct_kernel<16><<<(int)blocks, 256, smem, st>>>(a);
     B200_CUDA(cudaGetLastError());
     return 0;
