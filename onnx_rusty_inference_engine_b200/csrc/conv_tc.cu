@@ -20,7 +20,8 @@
 //     BN <= 64: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1) + four A stages;
 //     BN  > 64: one accumulator stage, four A stages; the epilogue drains TMEM to a shared-memory slab first and
 //     releases the accumulator before it touches global memory.
-// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 20 warps:
+// One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 28 warps in one of two role
+// layouts (struct Roles); the default one:
 //   warps 0-7   epilogue: warps w, w+4 share TMEM lanes 32*(w%4).. and take the two halves of the tile's channels.
 //               Phase 1 drains: tcgen05.ld main + correction, add, + bias (+ channel add), Relu, row-per-thread into a
 //               private swizzled slab; then the accumulator stage is handed back.  Phase 2 writes the slab out with
@@ -53,14 +54,22 @@ namespace {
 constexpr int BM = 128;                    // pixels per tile (UMMA M)
 constexpr int BK = 32;                     // floats per k-block (128 bytes)
 constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB (raw fp32 A tile of the pointwise mode)
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int TMA_WARP = 8;
-constexpr int MMA_WARP = 9;
-constexpr int ATMA_WARP = 10;   // pointwise layers: issues the TMA loads of the raw A tiles
-constexpr int NUM_PROD_WARPS = 16;  // two sets of 8: a set fills every other k-block
+// Warp roles, two layouts of the same 28 warps (EPI16 = template parameter of the kernel):
+//   EPI16 = false: 8 epilogue warps | TMA, MMA, A-TMA, idle | 16 A-producer warps (two sets of 8 that take alternate
+//                  k-blocks) -- layers that gather, and pointwise layers with a long reduction
+//   EPI16 = true : 16 epilogue warps | TMA, MMA, A-TMA, idle | 8 A-converter warps (every k-block) -- pointwise
+//                  layers with BN > 64 (expand1x1, conv10), whose epilogue is exposed or is the bound
+template <bool EPI16>
+struct Roles {
+  static constexpr int NEPI = EPI16 ? 16 : 8;       // epilogue warps (NEPI / 4 per TMEM lane quarter)
+  static constexpr int TMA_WARP = NEPI;
+  static constexpr int MMA_WARP = NEPI + 1;
+  static constexpr int ATMA_WARP = NEPI + 2;         // pointwise layers: issues the TMA loads of the raw A tiles
+  static constexpr int PROD_WARP0 = NEPI + 4;        // a multiple of 4: producer warp w writes TMEM lanes 32*(w%4)..
+  static constexpr int NSETS = EPI16 ? 1 : 2;        // producer sets of 8 warps; set j fills k-blocks j, j + NSETS, ...
+};
 constexpr int PROD_SET_WARPS = 8;
-constexpr int PROD_WARP0 = 12;  // a multiple of 4: producer warp w writes TMEM lanes 32*(w%4)..
-constexpr int NTHREADS = (PROD_WARP0 + NUM_PROD_WARPS) * 32;  // 896
+constexpr int NTHREADS = 28 * 32;  // 896
 constexpr int ROWS_PER_THREAD = 4;         // rows lane/4 + 8i of the warp's 32-row quarter
 constexpr int PREFETCH = 2;                // k-blocks of A loads in flight per producer thread (4 per SM-wide k-block stream)
 constexpr int A_STAGE_COLS = 64;           // TMEM columns per A stage: hi 32 | lo 32
@@ -224,10 +233,13 @@ __device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <bool HAS_ADD>
+template <bool HAS_ADD, bool EPI16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  using R_ = Roles<EPI16>;
+  constexpr int NUM_EPI_WARPS = R_::NEPI, TMA_WARP = R_::TMA_WARP, MMA_WARP = R_::MMA_WARP, ATMA_WARP = R_::ATMA_WARP,
+                PROD_WARP0 = R_::PROD_WARP0, NSETS = R_::NSETS;
   const ConvArgs& a = p.a;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_tile_bytes = p.BN * BK * 4;
@@ -299,7 +311,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     // k-blocks of the CTA's k-block stream (SA and R are even, so a set always meets the same A stages / raw
     // slots): a single warp's instruction stream was the pacing resource with 8 producer warps.
     const int pw = warp - PROD_WARP0;
-    const int quarter = pw & 3, khalf = (pw >> 2) & 1, kpar = pw >> 3;
+    const int quarter = pw & 3, khalf = (pw >> 2) & 1, kpar = pw >> 3;   // kpar < NSETS
     const int chunk = khalf * 4 + (lane & 3);
     const int rsub = lane >> 2;
     int my_tiles = 0;
@@ -321,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       }
       int r = kpar;
       uint32_t rph = 0;
-      for (int idx = kpar; idx < items; idx += 2) {
+      for (int idx = kpar; idx < items; idx += NSETS) {
         mbar_wait(raw_full(r), rph);
         const uint32_t raw = raw_ring + (uint32_t)r * A_TILE_BYTES;
         float4 x[ROWS_PER_THREAD];
@@ -340,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(raw_empty(r));
-        r += 2;
+        r += NSETS;
         if (r >= p.R) { r -= p.R; rph ^= 1u; }
         mbar_wait(empty_a(sa), ph ^ 1u);
         tc_fence_after();
@@ -357,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_a(sa));
-        sa += 2;
+        sa += NSETS;
         if (sa >= p.SA) { sa -= p.SA; ph ^= 1u; }
       }
     } else {
@@ -408,13 +420,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
         }
-        l_kb += 2;
+        l_kb += NSETS;
         if (l_kb >= p.nkb) {
           do { l_kb -= p.nkb; l_tile += gridDim.x; } while (l_kb >= p.nkb);
           if (l_tile < p.total_tiles) set_tile(l_tile);
         }
       };
-      const int my_items = (items - kpar + 1) >> 1;   // k-blocks this warp handles
+      const int my_items = (items - kpar + NSETS - 1) / NSETS;   // k-blocks this warp handles
       if (my_items > 0) set_tile(l_tile);
 #pragma unroll
       for (int d = 0; d < PREFETCH; ++d)
@@ -433,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(sa));
-            sa += 2;
+            sa += NSETS;
             if (sa >= p.SA) { sa -= p.SA; ph ^= 1u; }
           }
         }
@@ -530,16 +542,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       __syncwarp();
     }
   } else if (warp < NUM_EPI_WARPS) {
-    // ================================================================ epilogue (warps 0-7)
-    // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w and w+4 work on the same 32 accumulator rows and
+    // ================================================================ epilogue (warps 0 .. NUM_EPI_WARPS-1)
+    // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w, w+4, .. work on the same 32 accumulator rows and
     // take the 16-channel groups [g_begin, g_end) each.  Phase 1 (drain): per group tcgen05.ld main + correction,
     // add, + bias (+ channel add), Relu, and park the row in the warp's private slab (row per thread, 16-byte chunks
     // XOR-swizzled by row: conflict-free); then the accumulator stage goes back to the MMA warp.  Phase 2 (store):
     // consecutive lanes take consecutive 16-byte chunks of a row, so the global stores cover whole sectors of the
     // channels-last destination (which may be a channel slice of a Concat result).
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, part = warp >> 2;   // NUM_EPI_WARPS / 4 warps share a lane quarter and split its channels
+    constexpr int PARTS = NUM_EPI_WARPS / 4;
     const int G = p.BN >> 4;
-    const int g_begin = half ? (G + 1) >> 1 : 0, g_end = half ? G : (G + 1) >> 1;
+    const int g_begin = (G * part + PARTS - 1) / PARTS, g_end = (G * (part + 1) + PARTS - 1) / PARTS;
     const int ng = g_end - g_begin;            // 0..4 groups of 16 channels
     const int nchunk = ng * 4;                 // 16-byte chunks per slab row
     const uint32_t slab = epi_slabs + (uint32_t)(warp * 32 * p.slab_pitch);
@@ -777,13 +790,22 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.SA &= ~1;   // the two producer sets alternate k-blocks: even stage counts keep a set on its own stages
   // shared memory: weight ring, raw A ring (pointwise mode), epilogue slabs, per-channel constants, barriers
   const int stage_bytes = 2 * p.BN * BK * 4;
-  const int groups_per_warp = ((p.BN >> 4) + 1) >> 1;
-  p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
-  int fixed = 1024 + NUM_EPI_WARPS * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW) + 16;
   // Pointwise layers (1x1, stride 1, no padding): im2col row p IS input pixel p, so the A operand is a plain 2-D
   // matrix [P][C] and TMA can stream it; these layers are HBM-bound and want many bytes in flight.
   static const int no_atma = [] { const char* e = getenv("B200_TC_NO_ATMA"); return e ? atoi(e) : 0; }();
   p.a_tma = (!no_atma && a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.pt == 0 && a.pl == 0 && a.H == a.Ho && a.W == a.Wo) ? 1 : 0;
+  // Role layout: pointwise layers with wide tiles (BN > 64: one accumulator stage, so the drain is exposed, and for
+  // the expand1x1 layers a 128 x BN tile per ~1000 clk of MMAs) run with 16 epilogue warps and 8 converter warps --
+  // measured: conv10 0.210 -> 0.175 ms, expand1x1 3-6 % faster; squeeze layers (BN <= 64, HBM-bound) and BN = 64
+  // expands are better off with 8 + 16, like everything that gathers.
+  static const int force_epi16 = [] { const char* e = getenv("B200_TC_EPI16"); return e ? atoi(e) : -1; }();   // experiments only
+  bool epi16 = p.a_tma && p.BN > 64;
+  if (force_epi16 == 0) epi16 = false;
+  if (force_epi16 == 1) epi16 = p.a_tma != 0;
+  const int n_epi = epi16 ? 16 : 8;
+  const int groups_per_warp = ((p.BN >> 4) + n_epi / 4 - 1) / (n_epi / 4);
+  p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
+  int fixed = 1024 + n_epi * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW) + 16;
   p.R = 0;
   if (!p.a_tma) fixed += 128 * p.nkb;   // gather mode: the per-CTA k decode table
   int S = (SMEM_MAX - fixed) / stage_bytes;
@@ -794,7 +816,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
     if (S > 3) S = 3;
     int R = (SMEM_MAX - fixed - S * stage_bytes) / A_TILE_BYTES;
     if (R > MAX_RAW) R = MAX_RAW;
-    R &= ~1;   // same for the raw ring
+    if (!epi16) R &= ~1;   // same for the raw ring
     if (R < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for the raw A ring (BN=%d)", p.BN);
     p.R = R;
   }
@@ -814,8 +836,10 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   B200_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -834,8 +858,13 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
                      : CUDA_ERROR_NOT_SUPPORTED;
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
   }
-  if (a.chan_add) conv_tc_kernel<true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-  else conv_tc_kernel<false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  if (epi16) {
+    if (a.chan_add) conv_tc_kernel<true, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  } else {
+    if (a.chan_add) conv_tc_kernel<true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  }
   B200_CUDA(cudaGetLastError());
   return 0;
 }
