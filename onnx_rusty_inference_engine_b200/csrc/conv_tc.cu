@@ -310,6 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     // tile and the 16-byte chunk 4*khalf + lane%4 of each 128-byte k-block row.  The two sets take alternate
     // k-blocks of the CTA's k-block stream (SA and R are even, so a set always meets the same A stages / raw
     // slots): a single warp's instruction stream was the pacing resource with 8 producer warps.
+    if (EPI16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // converters only: no prefetch registers
     const int pw = warp - PROD_WARP0;
     const int quarter = pw & 3, khalf = (pw >> 2) & 1, kpar = pw >> 3;   // kpar < NSETS
     const int chunk = khalf * 4 + (lane & 3);
@@ -451,7 +452,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         }
       }
     }
-  } else if (warp == TMA_WARP) {
+  } else if (warp >= NUM_EPI_WARPS) {
+   // ================================================================ TMA / MMA / A-TMA / idle warpgroup
+   // these four warps need few registers: hand the rest to the epilogue warpgroups (setmaxnreg is warpgroup-wide)
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == TMA_WARP) {
     // ================================================================ weight tiles via TMA
     if (lane == 0) {
       int s = 0;
@@ -541,7 +546,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       if (leader) umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
       __syncwarp();
     }
-  } else if (warp < NUM_EPI_WARPS) {
+   }
+  } else {
+    // register budget (64 K per SM): 16 producer warps x 72 + 4 x 40 + 8 epilogue warps x 88, or
+    //                                  8 converter warps x 64 + 4 x 40 + 16 epilogue warps x 80
+    if (EPI16) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================================================ epilogue (warps 0 .. NUM_EPI_WARPS-1)
     // Warp w may only read TMEM lanes 32*(w % 4) .. +31, so warps w, w+4, .. work on the same 32 accumulator rows and
     // take the 16-channel groups [g_begin, g_end) each.  Phase 1 (drain): per group tcgen05.ld main + correction,
