@@ -64,18 +64,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived in [t0, t1] (perf_counter; the timed region).  nvidia-smi needs ~0.1 s to
+        start, so the sampler is started before the warm-up; a sample reports the state just before it is printed."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)   # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.03)]
+        window = "timed region"
+        if not rows:                       # region shorter than the sampling period: take the samples around it
+            rows = [r for (t, r) in self.rows if t0 is None or abs(t - t1) < 0.25]
+            window = "within 0.25 s of the timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -85,7 +93,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_rate(images: int, threads: int, seed: int = 11):
@@ -183,22 +191,24 @@ def run_own(args):
         if world > 1:  # the only collective: logits to every rank (8.2 MB at 8 x 256 x 1000)
             dist.all_gather_into_tensor(gathered, out)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(W):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    t_region0 = time.perf_counter()
     e0.record(stream)
     for i in range(K):
         step(i)
     e1.record(stream)
     torch.cuda.synchronize()
+    t_region1 = time.perf_counter()
     if world > 1:
         dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -206,7 +216,7 @@ def run_own(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = eng.ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     value = world * B * K / (ms / 1e3)
     assert torch.isfinite(out).all()
 
@@ -236,10 +246,9 @@ def run_own(args):
     if rank == 0:
         peaks = measured_peaks()
         # ---- roofline of the dominant kernel family (Conv), timed per launch with CUDA events on the launching
-        # stream inside the library (b200_model_profile), L2 flushed before every timed launch
-        # ("in_order": the launch list runs in model order and every launch is timed in place, so it sees the cache
-        # state it sees inside a timed step -- its input was just written by its predecessor; a step's activations
-        # exceed the L2.  profiles/ also holds the cold-cache variant, flush_l2=True.)
+        # stream inside the library (b200_model_profile, "in_order": the launch list runs in model order and every
+        # launch is timed in place, so it sees the cache state it sees inside a timed step -- its input was just
+        # written by its predecessor; a step's activations exceed the L2)
         prof = eng.model.profile(B, iters=5, flush_l2="in_order")
         conv = [p for p in prof if p["kind"].startswith("conv")]
         conv_ms = sum(p["ms"] for p in conv)
@@ -247,9 +256,17 @@ def run_own(args):
         total_ms = sum(p["ms"] for p in prof)
         top = max(prof, key=lambda p: p["ms"])
         tensor_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0   # TF32 = bf16/2; 3xTF32 = three MMAs per useful MAC
+        # The conv launches' duration INSIDE the timed region = the region's CUDA-event time per step x the conv
+        # launches' share of the per-launch event profile (isolated launches pay launch latency and clock ramps that a
+        # graph replay does not: their sum exceeds the step, their shares agree with the ncu launch list).
+        conv_share = conv_ms / total_ms if total_ms else 0.0
+        conv_ms_isolated = conv_ms
+        conv_ms = (ms / K) * conv_share
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         bw = [p for p in prof if not p["kind"].startswith("conv") and not p["kind"].startswith("matmul")]
         bw_ms = sum(p["ms"] for p in bw)
+        if total_ms:
+            bw_ms = (ms / K) * (bw_ms / total_ms)   # same apportioning for the bandwidth kernels
         bw_gbs = sum(p["bytes"] for p in bw) / (bw_ms * 1e-3) / 1e9 if bw_ms > 0 else None
         # DRAM bytes of the same launches from the committed ncu pass (profiles/README.md); null if absent
         traffic, traffic_src = None, None
@@ -264,10 +281,11 @@ def run_own(args):
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
             "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
-            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel), per-launch CUDA events in model order",
+            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel); duration = CUDA-event step time of the "
+                                                      "timed region x the launches' share of the in-order per-launch event profile",
             "kernel": f"conv (all {len(conv)} Conv launches of one step, 26 Conv nodes: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
             "peak_source": f"{peaks['src']}: bf16_tflops_sustained {peaks['bf16_tflops_sustained']} / 2 (TF32) / 3 (3xTF32)",
-            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / total_ms if total_ms else None,
+            "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_share, "conv_ms_isolated_launches": conv_ms_isolated,
             "top_launch": {"name": top["name"], "kind": top["kind"], "ms": top["ms"],
                            "tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else None},
             "hbm_ops": {"achieved_gbs": bw_gbs, "peak_gbs": peaks["hbm_gbs"],
@@ -280,7 +298,7 @@ def run_own(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             threads = max(1, min(cores, 64))
-            n_img = max(threads, 8)
+            n_img = max(8 * threads, 32)    # ~10-20 s of CPU work on this pool's hosts
             rate, dt = cpu_reference_rate(n_img, threads)
             cpu_line = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                         "sample": f"{n_img} images of the batch-{B} workload in {dt:.1f} s; C restatement of the "
