@@ -94,6 +94,7 @@ struct TcParams {
   int a_tma;       // 1: A tiles arrive by TMA into a raw ring (pointwise layers); 0: register gather
   int R;           // raw ring slots (a_tma)
   int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
+  uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
@@ -341,9 +342,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i)
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
-        // Split first: every split instruction consumes loaded values, so once they have issued the shared-memory
-        // reads are complete and the raw slot can go back to the TMA warp (releasing it right after issuing the
-        // ld.shared let the next TMA write overtake the reads).
         float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
@@ -351,8 +349,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           lo[i].x = split_lo(x[i].x, hi[i].x); lo[i].y = split_lo(x[i].y, hi[i].y);
           lo[i].z = split_lo(x[i].z, hi[i].z); lo[i].w = split_lo(x[i].w, hi[i].w);
         }
+        // The slot may be refilled by TMA as soon as raw_empty completes, so every ld.shared above must have READ it
+        // before the arrive is issued.  Having issued them is not enough (observed: with the input resident in L2 the
+        // refill overtook the last loads of a warp about once in 20 runs, rows 8i + lane/4 of one tile wrong), and the
+        // compiler sinks the split below the arrive.  So the arrive's address is made to depend on one register of
+        // each load: the instruction cannot issue before their scoreboards clear.  (The whole warp's loads are one
+        // instruction each, so lane 0's dependency covers the other lanes.)
+        // (p.zero is a kernel parameter that is always 0: an `& 0` literal would be folded away by ptxas)
+        const uint32_t dep = (__float_as_uint(x[0].w) ^ __float_as_uint(x[1].w) ^ __float_as_uint(x[2].w) ^ __float_as_uint(x[3].w)) & p.zero;
         __syncwarp();
-        if (lane == 0) mbar_arrive(raw_empty(r));
+        if (lane == 0) mbar_arrive(raw_empty(r) + dep);
         r += NSETS;
         if (r >= p.R) { r -= p.R; rph ^= 1u; }
         mbar_wait(empty_a(sa), ph ^ 1u);
@@ -803,6 +809,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.P = (int)P;
   p.n_tiles_n = w.Mpad / w.BN;
   p.reverse = a.reverse ? 1 : 0;
+  p.zero = 0;
   const long long tiles = ((P + BM - 1) / BM) * p.n_tiles_n;
   if (tiles >= (1ll << 31)) B200_FAIL(B200_EUNSUPPORTED, "too many tiles");
   p.total_tiles = (int)tiles;

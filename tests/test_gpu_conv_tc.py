@@ -84,3 +84,36 @@ def test_conv_tc_matches_cuda_core_path_in_fresh_process():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tc_check.py")], env=env, capture_output=True,
                            text=True, timeout=300)
         assert r.returncode == 0, f"conv path {path}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
+
+
+def test_conv_tc_power_of_two_scaling_full_size(ctx):
+    """Size-independent property at a BASELINE.json layer size (fire8 expand3x3, 64 images): without a bias,
+    conv(4 x) == 4 conv(x) bit for bit -- the hi / lo split, the tensor-core products and every fp32 add commute with a
+    power-of-two scaling -- and conv(0) == 0."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((64, 64, 27, 27)) * 3).astype(np.float32)
+    w = (rng.uniform(-1, 1, (256, 64, 3, 3)) / 24.0).astype(np.float32)
+    tw = ctx.tensor(w)
+    y1 = L.conv2d(ctx, ctx.tensor(x), tw, strides=(1, 1), pads=(1, 1, 1, 1)).numpy()
+    y4 = L.conv2d(ctx, ctx.tensor(4.0 * x), tw, strides=(1, 1), pads=(1, 1, 1, 1)).numpy()
+    assert y1.shape == (64, 256, 27, 27)
+    assert np.array_equal(y4, 4.0 * y1)
+    y0 = L.conv2d(ctx, ctx.tensor(np.zeros_like(x)), tw, strides=(1, 1), pads=(1, 1, 1, 1)).numpy()
+    assert not y0.any()
+
+
+def test_conv_tc_repeatable_pointwise_ring(ctx):
+    """Regression: the TMA-fed raw ring must not be refilled before every ld.shared of a converter warp has READ its
+    slot (not merely been issued).  With the input resident in L2 (repeated launches on 89 MB) the refill used to
+    overtake the last loads about once in 20 runs: fire9 squeeze, 16 k-blocks, ring of 8 slots wrapping twice per tile."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(1)
+    x = ctx.tensor((rng.standard_normal((256, 512, 13, 13)) * 3).astype(np.float32))
+    w = ctx.tensor((rng.standard_normal((64, 512, 1, 1)) * 0.05).astype(np.float32))
+    b = ctx.tensor(rng.standard_normal((64,)).astype(np.float32))
+    y = L.conv2d(ctx, x, w, bias=b, strides=(1, 1), pads=(0, 0, 0, 0), fuse_relu=True)
+    ref = y.numpy().copy()
+    for it in range(60):
+        L.conv2d(ctx, x, w, bias=b, strides=(1, 1), pads=(0, 0, 0, 0), fuse_relu=True, y=y)
+        assert np.array_equal(y.numpy(), ref), f"run {it} differs from the first"

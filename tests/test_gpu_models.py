@@ -109,6 +109,18 @@ def test_fire_fusion_matches_separate_launches(ctx, synth_onnx):
     assert_close(fused[:2], want, "fire fusion vs oracle")
 
 
+def test_alt_order_is_bitwise_neutral(ctx, synth_onnx):
+    """Launches that walk their tiles in alternating directions (L2 reuse) must give the same bits: tiles are independent."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    xs = synth.synthetic_batch(5, seed=9)
+    eng = Engine(synth_onnx, ctx=ctx)
+    a = eng(xs)
+    eng.model.set_option("alt_order", 0)
+    b = eng(xs)
+    assert np.array_equal(a, b)
+
+
 def test_squeezenet_batch_properties(ctx, synth_onnx):
     """Config 3 at full size (batch 256): batch-position invariance and softmax normalisation."""
     from onnx_rusty_inference_engine_b200 import synth
