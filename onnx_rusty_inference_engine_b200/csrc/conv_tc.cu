@@ -172,6 +172,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same, naming the registers the pending tcgen05.ld write: tcgen05.ld is asynchronous, and only a data dependency
+// keeps the compiler from scheduling arithmetic on those registers above the wait (a "memory" clobber orders memory
+// operations, not register uses).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]),
+                 "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]),
+                 "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]),
+                 "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
@@ -595,13 +607,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       if (PIPE && g_begin < g_end) {
         tmem_ld16(t_main + (uint32_t)(g_begin * 16), acc);
         tmem_ld16(t_main + (uint32_t)(p.BN + g_begin * 16), cor);
-        tmem_ld_wait();
+        tmem_ld_wait(acc, cor);
       }
       for (int g = g_begin; g < g_end; ++g) {
         if (!PIPE) {
           tmem_ld16(t_main + (uint32_t)(g * 16), acc);
           tmem_ld16(t_main + (uint32_t)(p.BN + g * 16), cor);
-          tmem_ld_wait();
+          tmem_ld_wait(acc, cor);
         }
         float o[16];
 #pragma unroll
@@ -640,7 +652,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((crow + 16u * q) ^ lane_sw), "f"(o[4 * q]), "f"(o[4 * q + 1]), "f"(o[4 * q + 2]), "f"(o[4 * q + 3]) : "memory");
-        if (PIPE && g + 1 < g_end) tmem_ld_wait();
+        if (PIPE && g + 1 < g_end) tmem_ld_wait(acc, cor);
       }
       // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp before storing
       tc_fence_before();
