@@ -123,13 +123,14 @@ __global__ void maxpool_kernel(PoolArgs a) {
 // per output instead of 9.  max is exact, so any association gives the reference's bits (zero-filled padding taps
 // and the -FLT_MAX fold start included).
 constexpr int kPoolStrip = 14;   // output rows per thread
+template <typename IDX>   // unsigned when the thread count fits 31 bits (32-bit divisions), else long long
 __global__ void maxpool3x3s2_kernel(PoolArgs a, int strips) {
   const int CV = a.C / 4;
-  const unsigned total = (unsigned)a.N * strips * a.Wo * CV;   // < 2^31, checked by the launcher
-  for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
-    const unsigned i = a.reverse ? total - 1u - j : j;
+  const IDX total = (IDX)a.N * strips * a.Wo * CV;
+  for (IDX j = (IDX)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (IDX)gridDim.x * blockDim.x) {
+    const IDX i = a.reverse ? total - 1 - j : j;
     const int c = (int)(i % CV);
-    unsigned t = i / CV;
+    IDX t = i / CV;
     const int wo = (int)(t % a.Wo);
     t /= a.Wo;
     const int strip = (int)(t % strips);
@@ -336,10 +337,11 @@ int launch_maxpool(const PoolArgs& a, cudaStream_t st) {
   const long long work = out_pixels * (vec ? a.C / 4 : a.C);
   const int grid = grid_for(work, kThreads, 32);
   static const int no_strip = [] { const char* e = getenv("B200_POOL_NO_STRIP"); return e ? atoi(e) : 0; }();   // A/B timing only
-  if (!no_strip && vec && small && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2) {
+  if (!no_strip && vec && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2) {
     const int strips = (a.Ho + kPoolStrip - 1) / kPoolStrip;
     const long long threads = (long long)a.N * strips * a.Wo * (a.C / 4);
-    maxpool3x3s2_kernel<<<grid_for(threads, kThreads, 32), kThreads, 0, st>>>(a, strips);
+    if (threads < (1ll << 31)) maxpool3x3s2_kernel<unsigned><<<grid_for(threads, kThreads, 32), kThreads, 0, st>>>(a, strips);
+    else maxpool3x3s2_kernel<long long><<<grid_for(threads, kThreads, 32), kThreads, 0, st>>>(a, strips);
     B200_CUDA(cudaGetLastError());
     return 0;
   }
