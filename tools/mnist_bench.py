@@ -12,6 +12,8 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 torch.cuda.set_device(0)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 eng = Engine(os.path.join(root, "tests", "golden", "mnist-8.onnx"), device=0, stream=s.cuda_stream)
+if os.environ.get("MNIST_CONV_PATH"):
+    eng.model.set_option("conv_path", int(os.environ["MNIST_CONV_PATH"]))
 x = torch.randn((B, 1, 28, 28), device="cuda") * 10
 out = torch.empty((B, 10), device="cuda")
 for _ in range(3):
