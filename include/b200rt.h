@@ -162,7 +162,8 @@ int b200_model_sync(b200_model *m);
 int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float *d_out);
 /* Options: "cuda_graph" (0/1, default 1), "conv_path" (0 = auto, 1 = force CUDA-core fp32 cross-check
  * kernel, 2 = force tcgen05 3xTF32), "fire_fusion" (0/1, default 1: expand1x1 + expand3x3 of a Fire module as one
- * launch when both fit one channel tile), "alt_order" (0/1, default 1: launches walk their tiles in alternating
+ * launch when both fit one channel tile), "s2d" (0/1, default 1: a stride-2 stem convolution runs on a 2x2
+ * space-to-depth copy of the graph input), "alt_order" (0/1, default 1: launches walk their tiles in alternating
  * directions so that each starts on what its predecessor left in the L2), "verbose" (0/1: print the reference's per-node lines). */
 int b200_model_set_option(b200_model *m, const char *key, int64_t value);
 /* Per-launch profile of the last planned batch size: runs each planned launch `iters` times between CUDA

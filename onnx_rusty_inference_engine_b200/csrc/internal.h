@@ -77,6 +77,8 @@ struct PoolArgs {
 // layout.cu
 int launch_nchw_to_rows(const float* src_nchw, TView dst, bool zero_pad_lanes, cudaStream_t st);
 int launch_rows_to_nchw(TView src, float* dst_nchw, cudaStream_t st);
+// NCHW [N,C,H,W] (H, W even) -> 2x2 space-to-depth rows [N, H/2, W/2, 4*C], channel (dy*2+dx)*C + c
+int launch_nchw_to_s2d(const float* src_nchw, int N, int C, int H, int W, float* dst, cudaStream_t st);
 int launch_copy_rows(TView src, TView dst, cudaStream_t st);          // same N,C,H,W; pitches may differ
 int launch_transpose2d(const float* src, int R, int C, float* dst, cudaStream_t st);  // dst[c][r] = src[r][c]
 // bandwidth_ops.cu

@@ -129,6 +129,68 @@ int launch_nchw_to_rows(const float* src, TView dst, bool zero_pad_lanes, cudaSt
   return 0;
 }
 
+// 2x2 space-to-depth of an NCHW tensor into channels-last rows: dst[((n*H2 + y)*W2 + x)*4C + (dy*2+dx)*C + c] =
+// src[((n*C + c)*H + 2y+dy)*W + 2x+dx].  Thread per (output pixel, 16-byte chunk), pixel fastest, so the plane reads of a
+// warp are runs of consecutive (dx = 0, 1) pairs.
+__global__ void nchw_to_s2d_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W, long long pixels /* N*H2*W2 */) {
+  const int W2 = W >> 1, H2 = H >> 1, CS = 4 * C, nq = CS >> 2;
+  const long long total = pixels * nq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % pixels;
+    const int q = (int)(i / pixels);
+    const int x = (int)(pix % W2);
+    const long long t = pix / W2;
+    const int y = (int)(t % H2);
+    const long long n = t / H2;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const int d = j / C, c = j - d * C;
+      v[e] = __ldg(src + ((n * C + c) * H + 2 * y + (d >> 1)) * (long long)W + 2 * x + (d & 1));
+    }
+    *reinterpret_cast<float4*>(dst + pix * CS + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// The same for C channels known at compile time (C = 3: the image stem): thread per output pixel, one 64-bit load per
+// (c, dy) -- a warp reads 256 contiguous bytes of an input row -- and 4*C/4 128-bit stores, 16*C contiguous bytes per pixel.
+template <int C>
+__global__ void nchw_to_s2d_fixed_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, long long pixels) {
+  const int W2 = W >> 1, H2 = H >> 1;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % W2);
+    const long long t = pix / W2;
+    const int y = (int)(t % H2);
+    const long long n = t / H2;
+    float v[4 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 pr = __ldg(reinterpret_cast<const float2*>(src + ((n * C + c) * H + 2 * y + dy) * (long long)W + 2 * x));
+        v[(dy * 2 + 0) * C + c] = pr.x;
+        v[(dy * 2 + 1) * C + c] = pr.y;
+      }
+    float4* o = reinterpret_cast<float4*>(dst + pix * (4 * C));
+#pragma unroll
+    for (int q = 0; q < C; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+int launch_nchw_to_s2d(const float* src, int N, int C, int H, int W, float* dst, cudaStream_t st) {
+  const long long pixels = (long long)N * (H / 2) * (W / 2);
+  if (pixels == 0 || C == 0) return 0;
+  if (C == 3 && (((uintptr_t)src) & 7) == 0 && (((uintptr_t)dst) & 15) == 0) {   // W even: every row pair is 8-byte aligned
+    nchw_to_s2d_fixed_kernel<3><<<grid_for(pixels, kThreads, 148 * 32), kThreads, 0, st>>>(src, dst, H, W, pixels);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
+  nchw_to_s2d_kernel<<<grid_for(pixels * C, kThreads, 148 * 32), kThreads, 0, st>>>(src, dst, C, H, W, pixels);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_rows_to_nchw(TView src, float* dst, cudaStream_t st) {
   const long long pixels = src.pixels();
   if (pixels == 0 || src.C == 0) return 0;

@@ -38,6 +38,7 @@ struct Val {  // one graph value for the planned batch
   TView v;
   bool planned = false;      // has a device location
   bool pad_zeroed = false;   // lanes [C, ld) are zero
+  bool s2d = false;          // graph input stored 2x2 space-to-depth: v is [N, H/2, W/2, 4*C], channel (dy*2+dx)*C + c
   bool is_init = false;      // initializer (constant)
   const WireTensor* init = nullptr;
   std::shared_ptr<std::vector<float>> host2d;  // constant rank-2 value produced by Reshape(initializer)
@@ -60,6 +61,8 @@ struct Plan {
   TView in_view;            // where the input transform writes
   bool in_zero_pad = false;
   bool in_direct = false;   // input needs no transform (C == 1 or H*W == 1): memcpy
+  bool in_s2d = false;      // input transform writes the 2x2 space-to-depth layout (stride-2 stem convolution)
+  int in_c0 = 0, in_h0 = 0, in_w0 = 0;   // logical C, H, W of the graph input (in_s2d)
   float* out_ptr = nullptr; // dense [batch, out_per_image]
   int64_t out_per_image = 0;
   bool out_needs_nchw = false;
@@ -90,7 +93,8 @@ struct b200_model {
   int opt_cuda_graph = 1;
   int opt_conv_path = 0;
   int opt_fire_fusion = 1;
-  int opt_alt_order = 1;     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
+  int opt_alt_order = 1;
+  int opt_s2d = 1;           // stride-2 stem convolution on a space-to-depth copy of the graph input     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
   int opt_verbose = 0;
   float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
   float* stage_out = nullptr; size_t stage_out_bytes = 0;
@@ -506,15 +510,38 @@ int Planner::do_conv(size_t i) {
   B200_TRY(place(out_name, &y));
   // ---- operand preparation
   float *dw = nullptr, *db = nullptr, *dadd = nullptr;
-  B200_TRY(conv_weights(*w->init, {M, C, KH, KW}, Ceff, &dw));
   if (bias) B200_TRY(vec_const(*bias, (size_t)M, &db));
   if (chan_add) B200_TRY(vec_const(*chan_add, (size_t)M, &dadd));
   ConvArgs a{};
-  a.x = x->v.p; a.N = x->v.N; a.C = Ceff; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
-  a.w = dw; a.M = M; a.KH = KH; a.KW = KW; a.K = KH * KW * Ceff; a.wc = Ceff; a.ldw = a.K;
+  if (x->s2d) {
+    // the stride-2 convolution over the space-to-depth input (Planner::run): kernel ceil(k/2)^2, 4*C channels, stride 1;
+    // W'[m][r][s][(dy*2+dx)*C + c] = W[m][c][2r+dy][2s+dx], zero where 2r+dy >= KH or 2s+dx >= KW
+    const int KH2 = (KH + 1) / 2, KW2 = (KW + 1) / 2, Cs = 4 * C;
+    std::string key = "convw:s2d:" + w->init->name;
+    if (m->consts.count(key)) dw = m->consts[key]->p;
+    else {
+      std::vector<float> h((size_t)M * KH2 * KW2 * Cs, 0.f);
+      for (int mm = 0; mm < M; ++mm)
+        for (int c = 0; c < C; ++c)
+          for (int r = 0; r < KH; ++r)
+            for (int sx = 0; sx < KW; ++sx)
+              h[(((size_t)mm * KH2 + r / 2) * KW2 + sx / 2) * Cs + ((r & 1) * 2 + (sx & 1)) * C + c] =
+                  w->init->f32[(((size_t)mm * C + c) * KH + r) * KW + sx];
+      B200_TRY(upload_const(m, key, h, &dw));
+    }
+    a.x = x->v.p; a.N = x->v.N; a.C = Cs; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
+    a.w = dw; a.M = M; a.KH = KH2; a.KW = KW2; a.K = KH2 * KW2 * Cs; a.wc = Cs; a.ldw = a.K;
+    a.sh = 1; a.sw = 1; a.pt = 0; a.pl = 0;
+    Ceff = Cs;   // keys the tcgen05 weight cache below
+  } else {
+    B200_TRY(conv_weights(*w->init, {M, C, KH, KW}, Ceff, &dw));
+    a.x = x->v.p; a.N = x->v.N; a.C = Ceff; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
+    a.w = dw; a.M = M; a.KH = KH; a.KW = KW; a.K = KH * KW * Ceff; a.wc = Ceff; a.ldw = a.K;
+    a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl;
+  }
   a.bias = db; a.chan_add = dadd;
   a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
-  a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl; a.relu = relu;
+  a.relu = relu;
   a.reverse = next_reverse();
   const double P = (double)y.v.pixels();
   const double flops = 2.0 * P * M * C * KH * KW;
@@ -524,7 +551,7 @@ int Planner::do_conv(size_t i) {
   if (m->opt_conv_path != 1 && tc_supported(a) == 0) {
     use_tc = true;
     if (!dry) {
-      std::string key = "tc:" + w->init->name + ":" + std::to_string(Ceff);
+      std::string key = "tc:" + w->init->name + ":" + std::to_string(Ceff) + (x->s2d ? ":s2d" : "");
       auto it = m->tc_weights.find(key);
       if (it == m->tc_weights.end()) {
         B200_TRY(tc_prepare_weights(dw, M, a.K, m->ctx->stream, &tcw));
@@ -815,12 +842,35 @@ int Planner::run() {
   in.dims[1] = m->in_dims[1]; in.dims[2] = m->in_dims[2]; in.dims[3] = m->in_dims[3];
   in.v.N = (int)in.dims[0]; in.v.C = (int)in.dims[1]; in.v.H = (int)in.dims[2]; in.v.W = (int)in.dims[3];
   in.v.ld = in.v.C >= 3 ? round_up4(in.v.C) : in.v.C;
+  // Stride-2 stem (SqueezeNet conv1: 7x7 / 2 on 3 channels): store the input 2x2 space-to-depth, [N, H/2, W/2, 4*C]
+  // with channel (dy*2+dx)*C + c.  The convolution becomes a stride-1 one with a ceil(k/2)^2 kernel over 4*C channels
+  // (do_conv builds the zero-padded weights): K = 4*4*12 = 192 = six full k-blocks instead of 7*7*4 = 196 (the
+  // channel-padded layout, seven k-blocks), 12 channels are three 16-byte chunks per tap, and the transform writes
+  // 25 % fewer bytes.  Exact: the extra taps have zero weights.
+  plan->in_s2d = false;
+  if (m->opt_s2d && m->opt_conv_path != 1 && in.v.C >= 1 && (4 * in.v.C) % 4 == 0 && in.v.H % 2 == 0 && in.v.W % 2 == 0) {
+    size_t jc = 0;
+    const WireNode* c = sole_consumer(m->input_name, &jc);
+    const WireTensor* w = (c && c->op_type == "Conv" && c->input.size() >= 2 && c->input[0] == m->input_name) ? m->wm.find_initializer(c->input[1]) : nullptr;
+    b200_conv_params cp;
+    if (w && parse_conv_attrs(*c, &cp) == 0 && cp.strides[0] == 2 && cp.strides[1] == 2 && cp.pads[0] == 0 && cp.pads[1] == 0 &&
+        cp.pads[2] == 0 && cp.pads[3] == 0 && (cp.auto_pad == B200_PAD_VALID || cp.auto_pad == B200_PAD_NOTSET)) {
+      auto wd = init_dims(m->wm, *w);
+      if (wd.size() == 4 && wd[1] == in.v.C && wd[2] >= 2 && wd[3] >= 2 && wd[2] <= 16 && wd[3] <= 16 && wd[2] <= in.v.H && wd[3] <= in.v.W &&
+          (int64_t)w->f32.size() == wd[0] * wd[1] * wd[2] * wd[3]) {
+        plan->in_s2d = true;
+        plan->in_c0 = in.v.C; plan->in_h0 = in.v.H; plan->in_w0 = in.v.W;
+        in.s2d = true;
+        in.v.C = 4 * in.v.C; in.v.H /= 2; in.v.W /= 2; in.v.ld = in.v.C;
+      }
+    }
+  }
   in.v.p = arena_alloc((size_t)in.v.pixels() * in.v.ld);
   in.planned = true; in.pad_zeroed = true;
   env[m->input_name] = in;
   plan->in_view = in.v;
-  plan->in_zero_pad = in.v.ld != in.v.C;
-  plan->in_direct = in.v.dense() && (in.v.C == 1 || in.v.H * in.v.W == 1);
+  plan->in_zero_pad = !plan->in_s2d && in.v.ld != in.v.C;
+  plan->in_direct = !plan->in_s2d && in.v.dense() && (in.v.C == 1 || in.v.H * in.v.W == 1);
 
   // Concat results need their dims before the producers run: shape-only evaluation happens naturally in
   // file order because each producer's `place` looks the parent up in env; so register Concat outputs
@@ -963,6 +1013,9 @@ int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out) {
   // 1. input: logical NCHW (what the reference's manage_input_data holds, utils.rs:29-45) -> channels-last rows
   if (plan->in_direct) {
     B200_CUDA(cudaMemcpyAsync(plan->in_view.p, d_in, (size_t)plan->in_view.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else if (plan->in_s2d) {
+    B200_TRY(launch_nchw_to_s2d(d_in, plan->in_view.N, plan->in_c0, plan->in_h0, plan->in_w0, plan->in_view.p, st));
+    m->ctx->launches++;
   } else {
     B200_TRY(launch_nchw_to_rows(d_in, plan->in_view, plan->in_zero_pad, st));
     m->ctx->launches++;
@@ -1059,6 +1112,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
   } else if (k == "fire_fusion") {
     if (m->opt_fire_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_fire_fusion = value ? 1 : 0;
+  } else if (k == "s2d") {
+    if (m->opt_s2d != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_s2d = value ? 1 : 0;
   } else if (k == "alt_order") {
     if (m->opt_alt_order != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_alt_order = value ? 1 : 0;

@@ -109,6 +109,23 @@ def test_fire_fusion_matches_separate_launches(ctx, synth_onnx):
     assert_close(fused[:2], want, "fire fusion vs oracle")
 
 
+def test_space_to_depth_stem_matches_plain_layout(ctx, synth_onnx):
+    """conv1 (7x7 / 2 on 3 channels) on the 2x2 space-to-depth copy of the input (a 4x4 / 1 convolution over 12 channels with
+    zero-padded weights) against the plain channel-padded layout and the oracle."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(3, seed=13)
+    eng = Engine(synth_onnx, ctx=ctx)
+    s2d = eng(xs)
+    eng.model.set_option("s2d", 0)
+    plain = eng(xs)
+    assert_close(s2d, plain, "space-to-depth stem vs plain layout")
+    want = rm.run_batch(ow.load_model(synth_onnx), xs[:2], threads=2)
+    assert_close(s2d[:2], want, "space-to-depth stem vs oracle")
+    assert (s2d.argmax(1) == plain.argmax(1)).all()
+
+
 def test_alt_order_is_bitwise_neutral(ctx, synth_onnx):
     """Launches that walk their tiles in alternating directions (L2 reuse) must give the same bits: tiles are independent."""
     from onnx_rusty_inference_engine_b200 import synth
