@@ -2,7 +2,7 @@
 usage: ncu_step_traffic.py launches.csv > profiles/<round>_step_dram_traffic.json
 The CSV comes from
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c N --csv
-A step starts at the input transform (nchw_to_rows*) and ends before the next one; the last COMPLETE step is kept."""
+A step starts at the input transform (nchw_to_rows* or nchw_to_s2d*) and ends before the next one; the last COMPLETE step is kept."""
 import csv, json, sys
 
 rows = []
@@ -27,7 +27,7 @@ for r in rows:
     elif name == "dram__bytes_write.sum":
         launches[i]["dram_write"] = v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
 seq = [launches[i] for i in order]
-starts = [k for k, l in enumerate(seq) if "nchw_to_rows" in l["kernel"]]
+starts = [k for k, l in enumerate(seq) if "nchw_to_" in l["kernel"]]
 # the last start that is followed by a gap_softmax launch is the last complete step
 step = None
 for s in reversed(starts):
