@@ -95,7 +95,7 @@ struct TcParams {
   int R;           // raw ring slots (a_tma)
   int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
-  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st
+  int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -514,7 +514,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     // The issue stream is a critical resource (measured: while descriptors were rebuilt from addresses inside a
     // single-lane branch the time per k-block did not depend on BN), so the 64-bit shared-memory descriptors are
     // kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
-    const uint32_t idesc = instr_desc_tf32(p.BN), idesc2 = instr_desc_tf32(2 * p.BN);
+    // B200_TC_DEBUG bit 256 (timing experiment): issue every MMA with N = 16, whatever BN is
+    const uint32_t idesc = instr_desc_tf32((p.debug & 256) ? 16 : p.BN), idesc2 = instr_desc_tf32((p.debug & 256) ? 16 : 2 * p.BN);
     const bool leader = elect_one();
     const uint32_t lo_first = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
     const uint32_t lo_step = (uint32_t)stage_bytes >> 4;
