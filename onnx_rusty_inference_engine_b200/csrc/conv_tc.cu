@@ -29,9 +29,12 @@
 //   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the weight tiles.
 //   warp 9      MMA issuer (uniform control flow, one elected lane, descriptors advanced by adds).
 //   warp 10     pointwise layers: TMA loads of raw fp32 A tiles into a shared-memory ring.
-//   warps 12-19 A producers: warp w owns TMEM lanes 32*(w%4).. (hardware rule) and the 64-byte half (w-12)/4 of each
-//               k-block row.  Gather mode: im2col rows straight from the channels-last activation (any stride /
-//               padding / tap; 3 k-blocks of loads in flight per thread).  Pointwise mode: read the TMA-fed raw tile.
+//   warps 12-27 A producers, two sets of 8 that take alternate k-blocks: warp w owns TMEM lanes 32*(w%4).. (hardware
+//               rule) and the 64-byte half ((w-12)/4)%2 of each k-block row.  Gather mode: im2col rows straight from
+//               the channels-last activation (any stride / padding / tap; (r, s, offset) of a chunk from a per-CTA
+//               table; 2 k-blocks of loads in flight per thread).  Pointwise mode: read the TMA-fed raw tile.
+// The second layout (pointwise layers with BN > 64): 16 epilogue warps, 8 converter warps.  The 896 threads start at 72
+// registers; setmaxnreg then gives the TMA/MMA warpgroup 40, the epilogue warpgroups 88 (80) and the converters 64.
 // Weights are split, permuted, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
 #include <cuda.h>
 
