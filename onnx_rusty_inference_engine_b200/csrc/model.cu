@@ -102,7 +102,7 @@ struct b200_model {
   struct Slot {
     float* in = nullptr; size_t in_bytes = 0;
     float* out = nullptr; size_t out_bytes = 0;
-    cudaEvent_t in_ready = nullptr, done = nullptr, out_done = nullptr;
+    cudaEvent_t in_ready = nullptr, in_free = nullptr, done = nullptr, out_done = nullptr;
   } slots[2];
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint64_t seq = 0;
@@ -113,6 +113,7 @@ struct b200_model {
       if (sl.in) cudaFree(sl.in);
       if (sl.out) cudaFree(sl.out);
       if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+      if (sl.in_free) cudaEventDestroy(sl.in_free);
       if (sl.done) cudaEventDestroy(sl.done);
       if (sl.out_done) cudaEventDestroy(sl.out_done);
     }
@@ -1008,7 +1009,8 @@ int run_steps(b200_model* m, Plan* plan, cudaStream_t st) {
   return 0;
 }
 
-int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out) {
+// `input_consumed` (optional) is recorded right after the input transform: from then on d_in may be overwritten
+int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out, cudaEvent_t input_consumed = nullptr) {
   cudaStream_t st = m->ctx->stream;
   // 1. input: logical NCHW (what the reference's manage_input_data holds, utils.rs:29-45) -> channels-last rows
   if (plan->in_direct) {
@@ -1020,6 +1022,7 @@ int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out) {
     B200_TRY(launch_nchw_to_rows(d_in, plan->in_view, plan->in_zero_pad, st));
     m->ctx->launches++;
   }
+  if (input_consumed) B200_CUDA(cudaEventRecord(input_consumed, st));
   // 2. the node walk, replayed as one CUDA graph
   if (m->opt_cuda_graph) {
     if (!plan->graph_exec) {
@@ -1170,6 +1173,7 @@ int b200_model_run_async(b200_model* m, const float* host_in, int64_t batch, flo
     B200_CUDA(cudaStreamCreateWithFlags(&m->d2h, cudaStreamNonBlocking));
     for (auto& sl : m->slots) {
       B200_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+      B200_CUDA(cudaEventCreateWithFlags(&sl.in_free, cudaEventDisableTiming));
       B200_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
       B200_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
     }
@@ -1193,14 +1197,14 @@ int b200_model_run_async(b200_model* m, const float* host_in, int64_t batch, flo
     }
   }
   cudaStream_t st = m->ctx->stream;
-  // H2D of this batch overlaps the compute of the previous one; the slot's previous occupant must have been
-  // consumed (input transform done) and drained (logits copied out) first
-  if (reused) { B200_CUDA(cudaStreamWaitEvent(m->h2d, sl.done, 0)); }
+  // H2D of this batch overlaps the compute of the previous one (and of the one before: the slot's input buffer is
+  // free as soon as its previous occupant's input transform has run, so the copy engine never waits for a whole run)
+  if (reused) { B200_CUDA(cudaStreamWaitEvent(m->h2d, sl.in_free, 0)); }
   B200_CUDA(cudaMemcpyAsync(sl.in, host_in, in_bytes, cudaMemcpyHostToDevice, m->h2d));
   B200_CUDA(cudaEventRecord(sl.in_ready, m->h2d));
   B200_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
   if (reused) { B200_CUDA(cudaStreamWaitEvent(st, sl.out_done, 0)); }
-  B200_TRY(run_plan(m, p, sl.in, sl.out));
+  B200_TRY(run_plan(m, p, sl.in, sl.out, sl.in_free));
   B200_CUDA(cudaEventRecord(sl.done, st));
   B200_CUDA(cudaStreamWaitEvent(m->d2h, sl.done, 0));
   B200_CUDA(cudaMemcpyAsync(host_out, sl.out, out_bytes, cudaMemcpyDeviceToHost, m->d2h));
