@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kGapThreads) gap_softmax_kernel(const float* _
   for (int g = threadIdx.x & 255; g < G; g += 256) {
     if (VEC) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 11
       for (int k = sl; k < HW; k += kGapSlices) {
         const float4 v = ldg4(xin + (long long)k * ldx + g * 4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
