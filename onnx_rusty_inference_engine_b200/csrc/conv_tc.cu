@@ -77,6 +77,7 @@ constexpr int ROWS_PER_THREAD = 4;         // rows lane/4 + 8i of the warp's 32-
 constexpr int PREFETCH = 2;                // k-blocks of A loads in flight per producer thread (4 per SM-wide k-block stream)
 constexpr int A_STAGE_COLS = 64;           // TMEM columns per A stage: hi 32 | lo 32
 constexpr int MAX_A_STAGES = 4;
+constexpr int MERGED_MAX_K = 288;          // longest reduction that uses one merged accumulator (see launch_conv_tc)
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 6;              // weight ring
 constexpr int MAX_RAW = 8;                 // raw A ring (pointwise / TMA-fed mode)
@@ -86,7 +87,9 @@ struct TcParams {
   int BN;          // output channels per tile (multiple of 16, <= 128)
   int S;           // weight ring stages (shared memory)
   int SA;          // A stages (tensor memory)
-  int nacc;        // accumulator stages (tensor memory): 2 when 4*BN + 2*64 <= 512, else 1
+  int nacc;        // accumulator stages (tensor memory)
+  int merged;      // 1: hi*hi, hi*lo and lo*hi accumulate into ONE accumulator of BN columns (three N = BN MMAs per k-step);
+                   // 0: {main | correction} accumulators of BN columns each (one N = 2*BN and one N = BN MMA per k-step)
   int nkb;         // k-blocks per tile
   int n_tiles_n;   // channel tiles
   int reverse;     // walk the tiles from the last to the first (see ConvArgs::reverse)
@@ -275,7 +278,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   auto raw_full = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + r); };
   auto raw_empty = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + MAX_RAW + r); };
   const uint32_t ktab = (raw_empty(MAX_RAW) + 15u) & ~15u;   // gather mode: nkb x 8 entries {delta, r, s, valid mask}
-  const int a_col0 = p.nacc * 2 * p.BN;   // first TMEM column of the A stages
+  const int acc_cols = p.merged ? p.BN : 2 * p.BN;   // TMEM columns per accumulator stage
+  const int a_col0 = p.nacc * acc_cols;   // first TMEM column of the A stages
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -533,8 +537,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
       mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
       tc_fence_after();
-      const uint32_t d_main = tmem_base + (uint32_t)(as * 2 * p.BN);
-      const uint32_t d_corr = d_main + (uint32_t)p.BN;
+      const uint32_t d_main = tmem_base + (uint32_t)(as * acc_cols);
+      const uint32_t d_corr = p.merged ? d_main : d_main + (uint32_t)p.BN;
+      const uint32_t b_lo = (uint32_t)b_tile_bytes >> 4;   // B_lo follows B_hi in the stage (descriptor units of 16 bytes)
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(full_a(sa), pha);  // A stage written to tensor memory by all 8 producer warps
         mbar_wait(full_b(s), ph);
@@ -546,13 +551,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           // B_hi and B_lo are adjacent in the stage ([2*BN rows] x 128 B), and so are the two accumulators
           // ([main | correction] = 2*BN TMEM columns): ONE N = 2*BN instruction computes A_hi*B_hi -> main and
           // A_hi*B_lo -> correction; a second N = BN instruction adds A_lo*B_hi.
-          umma_tf32_ts(d_main, ah, sw128_desc(bh), idesc2, kb != 0 ? 1u : 0u);
-          umma_tf32_ts(d_corr, al, sw128_desc(bh), idesc, 1u);
+          // Merged mode (BN > 64, where {main | correction} x 2 stages would not fit tensor memory): three N = BN
+          // instructions per k-step into one accumulator -- the same tensor-pipe time, and two accumulator stages fit.
+          if (p.merged) {
 #pragma unroll
-          for (int kk = 1; kk < 4; ++kk) {
-            if (kk < ksteps) {
-              umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + 2 * kk), idesc2, 1u);
-              umma_tf32_ts(d_corr, al + 8u * kk, sw128_desc(bh + 2 * kk), idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < ksteps) {
+                umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + 2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + b_lo + 2 * kk), idesc, 1u);
+                umma_tf32_ts(d_main, al + 8u * kk, sw128_desc(bh + 2 * kk), idesc, 1u);
+              }
+            }
+          } else {
+            umma_tf32_ts(d_main, ah, sw128_desc(bh), idesc2, kb != 0 ? 1u : 0u);
+            umma_tf32_ts(d_corr, al, sw128_desc(bh), idesc, 1u);
+#pragma unroll
+            for (int kk = 1; kk < 4; ++kk) {
+              if (kk < ksteps) {
+                umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + 2 * kk), idesc2, 1u);
+                umma_tf32_ts(d_corr, al + 8u * kk, sw128_desc(bh + 2 * kk), idesc, 1u);
+              }
             }
           }
         }
@@ -601,22 +619,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       const int m0 = (tt % p.n_tiles_n) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * 2 * p.BN);
+      const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
+      const bool two_acc = !p.merged;
       // software-pipelined drain (the extra registers come from setmaxnreg): the tcgen05.ld of group g+1 is in flight
       // while group g gets its bias / Relu and goes to the slab
       // (gather layers: conv1 0.635 -> 0.608 ms; the 16-epilogue-warp layout is better off without it: expand1x1
       // 0.084 -> 0.098 ms with it)
       constexpr bool PIPE = !EPI16;
       uint32_t acc[16], cor[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cor[j] = 0u;   // merged mode: no correction accumulator, acc + 0 is exact
       if (PIPE && g_begin < g_end) {
         tmem_ld16(t_main + (uint32_t)(g_begin * 16), acc);
-        tmem_ld16(t_main + (uint32_t)(p.BN + g_begin * 16), cor);
+        if (two_acc) tmem_ld16(t_main + (uint32_t)(p.BN + g_begin * 16), cor);
         tmem_ld_wait(acc, cor);
       }
       for (int g = g_begin; g < g_end; ++g) {
         if (!PIPE) {
           tmem_ld16(t_main + (uint32_t)(g * 16), acc);
-          tmem_ld16(t_main + (uint32_t)(p.BN + g * 16), cor);
+          if (two_acc) tmem_ld16(t_main + (uint32_t)(p.BN + g * 16), cor);
           tmem_ld_wait(acc, cor);
         }
         float o[16];
@@ -624,7 +645,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);   // hi*hi + (lo*hi + hi*lo)
         if (PIPE && g + 1 < g_end) {
           tmem_ld16(t_main + (uint32_t)((g + 1) * 16), acc);
-          tmem_ld16(t_main + (uint32_t)(p.BN + (g + 1) * 16), cor);
+          if (two_acc) tmem_ld16(t_main + (uint32_t)(p.BN + (g + 1) * 16), cor);
         }
         const uint32_t boff = 4u * (uint32_t)(m0 + g * 16);
         const uint32_t crow = my_row + ((uint32_t)(g - g_begin) << 6);
@@ -834,9 +855,19 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   // two accumulator stages only when four A stages still fit beside them (BN <= 64): measured on BN = 96 (conv1,
   // fire6/7 expand3x3), four A stages + one accumulator stage beat two + two by 11-15 %
   p.nacc = (4 * p.BN + MAX_A_STAGES * A_STAGE_COLS <= 512) ? 2 : 1;
+  // BN > 64: one merged accumulator per stage, so two stages of BN columns + four A stages fit (2*128 + 4*64 = 512)
+  static const int force_merged = [] { const char* e = getenv("B200_TC_MERGED"); return e ? atoi(e) : -1; }();   // experiments only
+  // The tensor core truncates when it adds into the fp32 accumulator (measured: error grows linearly with the number
+  // of accumulating instructions, ~0.5 ulp of the accumulator each), and merging triples the additions into the large
+  // accumulator.  So merge only while 3*K/8 additions stay near what the longest unmerged reduction of the model
+  // performs (K = 576: 72): K <= 288 -> <= 108.  Longer reductions amortise the exposed drain anyway.
+  p.merged = (p.BN > 64 && a.K <= MERGED_MAX_K) ? 1 : 0;
+  if (force_merged == 0 || force_merged == 1) p.merged = force_merged;
+  const int acc_cols = p.merged ? p.BN : 2 * p.BN;
+  if (p.merged) p.nacc = 2;
   if (force_nacc == 1 || force_nacc == 2) p.nacc = force_nacc;
-  if (4 * p.BN + 2 * A_STAGE_COLS > 512) p.nacc = 1;
-  p.SA = (512 - p.nacc * 2 * p.BN) / A_STAGE_COLS;
+  if (p.nacc * acc_cols + 2 * A_STAGE_COLS > 512) p.nacc = 1;
+  p.SA = (512 - p.nacc * acc_cols) / A_STAGE_COLS;
   if (p.SA > MAX_A_STAGES) p.SA = MAX_A_STAGES;
   p.SA &= ~1;   // the two producer sets alternate k-blocks: even stage counts keep a set on its own stages
   // shared memory: weight ring, raw A ring (pointwise mode), epilogue slabs, per-channel constants, barriers

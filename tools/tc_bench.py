@@ -16,6 +16,7 @@ LAYERS = {  # name: (N, C, H, W, M, k, stride, pad)
     "f8_sq": (256, 384, 27, 27, 64, 1, 1, 0),
     "f8_e3": (256, 64, 27, 27, 256, 3, 1, 1),
     "conv10": (256, 512, 13, 13, 1000, 1, 1, 0),
+    "f2_fused": (256, 16, 54, 54, 128, 3, 1, 1),   # fire2 expand1x1 + expand3x3 as one launch (planner fusion)
     "f5_e1": (256, 32, 27, 27, 128, 1, 1, 0),
     "f6_e1": (256, 48, 27, 27, 192, 1, 1, 0),
     "f6_e3": (256, 48, 27, 27, 192, 3, 1, 1),
