@@ -224,13 +224,17 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-// The producer's version of the same split, 4 integer/FP instructions per element instead of the ~10 that two
-// cvt.rna.tf32 expand to (the PTX conversion is emulated with NaN/Inf handling on sm_100):
-//   hi = (bits(x) + 0x1000) & 0xFFFFE000      round-to-nearest (ties away) to 10 mantissa bits, exact TF32 value
-//   lo = bits(x - hi) + 0x1000                the tensor core ignores the low 13 bits of a TF32 operand, so adding
-//                                             half an ulp before that truncation IS the rounding; no mask needed
-__device__ __forceinline__ float split_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ float split_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) + 0x1000u); }
+// The producer's split, 2 instructions per element (the producers are issue-bound on the gather layers: in the conv1
+// capture they were busy 80 % of the time and the split was a third of their k-block loop):
+//   hi = bits(x) & 0xFFFFE000      truncation to 10 mantissa bits, an exact TF32 value
+//   lo = x - hi                    exact in fp32 (13 significant bits, sign of x); the tensor core reads its top 10
+//                                  mantissa bits
+// x = hi + lo holds exactly whatever the rounding of hi, so the only cost against the round-to-nearest split used for
+// the weights is the representation error of lo: <= 2^-21 |x| instead of 2^-23 |x|, i.e. a relative 2.4e-7 on a
+// product (mean 1.2e-7, the same sign on every term: a scale factor on the output, four hundred times below the 1e-4
+// relative tolerance) -- measured with tools/exp/merged_error.py: rms error against fp64 unchanged to two digits.
+__device__ __forceinline__ float split_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float split_lo(float x, float hi) { return x - hi; }
 
 // A producer's four 16-byte chunks (rows lane/4 + 8i of its 32-row quarter) are split into hi / lo and written to the
 // warp's part of an A stage in tensor memory: hi -> columns [0,32), lo -> [32,64) of the stage; t_stage = lane
