@@ -116,6 +116,34 @@ def build_squeezenet(seed: int = 0, raw: bool = True) -> bytes:
     return P.encode("ModelProto", model)
 
 
+def build_fire(cin: int, squeeze: int, expand: int, hw: int, seed: int = 0) -> bytes:
+    """One Fire module on its own (test model): data_0 [1, cin, hw, hw] -> squeeze 1x1 -> {expand 1x1, expand 3x3 pad 1}
+    -> Concat, which is the graph output.  Weights scaled so that activations stay O(input)."""
+    rng = np.random.default_rng(seed)
+    nodes: List[Dict] = []
+    inits: List[Dict] = []
+    inputs: List[Dict] = [P.make_value_info("data_0", [1, cin, hw, hw])]
+
+    def conv(name: str, x: str, ci: int, co: int, k: int, pad: int) -> str:
+        b = np.sqrt(6.0 / (ci * k * k))
+        for nm, arr in ((f"{name}_w_0", rng.uniform(-b, b, size=(co, ci, k, k))), (f"{name}_b_0", rng.uniform(-0.1, 0.1, size=(co,)))):
+            inits.append(P.make_tensor(nm, arr.astype(np.float32), raw=True))
+            inputs.append(P.make_value_info(nm, arr.shape))
+        nodes.append(P.make_node("Conv", [x, f"{name}_w_0", f"{name}_b_0"], [f"{name}_1"], name=name,
+                                 kernel_shape=[k, k], strides=[1, 1], pads=[pad] * 4))
+        nodes.append(P.make_node("Relu", [f"{name}_1"], [f"{name}_2"], name=f"{name}_relu"))
+        return f"{name}_2"
+
+    sq = conv("fire_squeeze1x1", "data_0", cin, squeeze, 1, 0)
+    e1 = conv("fire_expand1x1", sq, squeeze, expand, 1, 0)
+    e3 = conv("fire_expand3x3", sq, squeeze, expand, 3, 1)
+    nodes.append(P.make_node("Concat", [e1, e3], ["fire_concat_1"], name="fire_concat", axis=1))
+    graph = {"node": nodes, "name": "fire-synth", "initializer": inits, "input": inputs,
+             "output": [P.make_value_info("fire_concat_1", [1, 2 * expand, hw, hw])]}
+    model = {"ir_version": 3, "producer_name": "b200-synth", "graph": graph, "opset_import": [{"domain": "", "version": 8}]}
+    return P.encode("ModelProto", model)
+
+
 def ensure_squeezenet(path: str, seed: int = 0) -> str:
     """Write the synthetic model to `path` if it is not there yet (deterministic for a given seed)."""
     if not os.path.exists(path):

@@ -109,6 +109,38 @@ def test_fire_fusion_matches_separate_launches(ctx, synth_onnx):
     assert_close(fused[:2], want, "fire fusion vs oracle")
 
 
+@pytest.mark.parametrize("cin,squeeze,expand,hw,batch,fuses", [
+    (8, 16, 64, 17, 4, True),       # fire2-like: both branches in one channel tile -> one launch
+    (24, 32, 128, 11, 5, False),    # fire4-like: K = 288 (merged accumulator), ragged last pixel tile
+    (16, 48, 192, 9, 7, False),     # fire6-like: channel tiles of 96
+    (16, 64, 256, 13, 3, False),    # fire8-like: two channel tiles of 128, 18 k-blocks
+])
+def test_fire_module_alone(ctx, tmp_path, cin, squeeze, expand, hw, batch, fuses):
+    """A Fire module as a model of its own, so the Concat result itself (channel-slice writes of both branches) is compared
+    with the oracle element by element, with and without the expand fusion."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    path = str(tmp_path / "fire.onnx")
+    with open(path, "wb") as f:
+        f.write(synth.build_fire(cin, squeeze, expand, hw, seed=cin + expand))
+    # unit-variance input: activations stay O(1), the scale at which the absolute 1e-5 term of the tolerance is meant
+    xs = synth.synthetic_batch(batch, chw=(cin, hw, hw), seed=expand, std=1.0)
+    want = rm.run_batch(ow.load_model(path), xs, threads=2)
+    eng = Engine(path, ctx=ctx)
+    assert eng.out_per_image == 2 * expand * hw * hw
+    fused = eng(xs)
+    n_fused = eng.model.launches_per_run(batch)
+    assert_close(fused.reshape(want.shape), want, "fire module vs oracle")
+    eng.model.set_option("fire_fusion", 0)
+    separate = eng(xs)
+    assert eng.model.launches_per_run(batch) == n_fused + (1 if fuses else 0)
+    assert_close(separate.reshape(want.shape), want, "separate fire launches vs oracle")
+    eng.model.set_option("fire_fusion", 1)
+    eng.model.set_option("alt_order", 0)
+    assert np.array_equal(eng(xs), fused), "tile walking direction must not change the bits"
+
+
 def test_space_to_depth_stem_matches_plain_layout(ctx, synth_onnx):
     """conv1 (7x7 / 2 on 3 channels) on the 2x2 space-to-depth copy of the input (a 4x4 / 1 convolution over 12 channels with
     zero-padded weights) against the plain channel-padded layout and the oracle."""
