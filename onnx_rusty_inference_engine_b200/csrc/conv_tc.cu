@@ -77,6 +77,13 @@ constexpr int ROWS_PER_THREAD = 4;         // rows lane/4 + 8i of the warp's 32-
 constexpr int PREFETCH = 2;                // k-blocks of A loads in flight per producer thread (4 per SM-wide k-block stream)
 constexpr int A_STAGE_COLS = 64;           // TMEM columns per A stage: hi 32 | lo 32
 constexpr int MAX_A_STAGES = 4;
+// B200_TC_DEBUG role masks (timing experiments, tools/exp/sweep_*.sh) are compiled in only with -DB200_TC_DEBUG_MASKS=1
+// (`make debug` -> lib/variants/libb200rt_dbg.so, selected with B200RT_LIB): the producers are instruction-bound, and
+// the mask tests sat in their inner loop.
+#ifndef B200_TC_DEBUG_MASKS
+#define B200_TC_DEBUG_MASKS 0
+#endif
+#define TC_DBG(bit) (B200_TC_DEBUG_MASKS && (p.debug & (bit)))
 constexpr int MERGED_MAX_K = 288;          // longest reduction that uses one merged accumulator (see launch_conv_tc)
 constexpr int SMEM_MAX = 227 * 1024;
 constexpr int MAX_STAGES = 6;              // weight ring
@@ -102,6 +109,8 @@ struct TcParams {
   int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
+  int nopad;       // every tap of every output pixel lies inside the image: no validity masks (gather mode)
+  unsigned long long m64Wo, m64Ho;   // ceil(2^64 / d), 0 when d == 1: exact n / d for n < 2^32 by one multiply-high
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -386,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         if (r >= p.R) { r -= p.R; rph ^= 1u; }
         mbar_wait(empty_a(sa), ph ^ 1u);
         tc_fence_after();
-        if (!(p.debug & 32)) {
+        if (!TC_DBG(32)) {
           const uint32_t t_stage = t_a0 + (uint32_t)(sa * A_STAGE_COLS);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -415,13 +424,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
         // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
         const int p0 = ((p.reverse ? p.total_tiles - 1 - tile : tile) / p.n_tiles_n) * BM;
-        const int t0 = p0 / a.Wo, wo0 = p0 - t0 * a.Wo;
-        const int n0 = t0 / a.Ho, ho0 = t0 - n0 * a.Ho;
+        const int t0 = p.m64Wo ? (int)__umul64hi((unsigned long long)p0, p.m64Wo) : p0, wo0 = p0 - t0 * a.Wo;
+        const int n0 = p.m64Ho ? (int)__umul64hi((unsigned long long)t0, p.m64Ho) : t0, ho0 = t0 - n0 * a.Ho;
         hmask = 0; wmask = 0;
+        const int last_row = p.P - 1 - p0;   // rows past the last pixel (last tile only)
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          const int row = quarter * 32 + i * 8 + rsub;
-          const bool ok = p0 + row < p.P;
+          int row = quarter * 32 + i * 8 + rsub;
+          const bool ok = row <= last_row;
+          if (p.nopad) row = min(row, last_row);   // no masks: a row past the end re-reads the last pixel (never stored)
           const int wsum = wo0 + row;
           const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
           const int wo = wsum - cw * a.Wo;
@@ -431,24 +442,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           const int n = n0 + ch;
           const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
           base[i] = ((n * a.H + h0) * a.W + w0) * a.ldx;   // may be "negative" for padded taps: never dereferenced then
-          // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
-          const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
-          const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
-          const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
-          const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
-          hmask |= hm << (8 * i);
-          wmask |= wm << (8 * i);
+          if (!p.nopad) {
+            // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
+            const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
+            const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
+            const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
+            const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
+            hmask |= hm << (8 * i);
+            wmask |= wm << (8 * i);
+          }
         }
       };
       float4 v[PREFETCH][ROWS_PER_THREAD];
       auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
         uint32_t delta, r, sx, vm;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(delta), "=r"(r), "=r"(sx), "=r"(vm) : "r"(ktab + 16u * (uint32_t)(l_kb * 8 + chunk)));
-        const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
+        if (p.nopad) {
+          // every tap is inside the image: four plain loads (vm = 0 only for the chunks past K in the last k-block)
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (((m >> (8 * i)) & 1u) && !(p.debug & 2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vm && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+          }
+        } else {
+          const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+          }
         }
         l_kb += NSETS;
         if (l_kb >= p.nkb) {
@@ -469,7 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           if (it < my_items) {
             mbar_wait(empty_a(sa), ph ^ 1u);   // the MMAs that read this A stage have completed
             tc_fence_after();
-            if (!(p.debug & 32)) split_store(t_a0 + (uint32_t)(sa * A_STAGE_COLS), v[d]);
+            if (!TC_DBG(32)) split_store(t_a0 + (uint32_t)(sa * A_STAGE_COLS), v[d]);
             if (it + PREFETCH < my_items) issue(v[d]);   // next loads go out before the store wait
             tmem_st_wait();
             tc_fence_before();
@@ -495,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(empty_b(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
-          if (p.debug & 1) { mbar_arrive(full_b(s)); if (++s == p.S) { s = 0; ph ^= 1u; } continue; }
+          if (TC_DBG(1)) { mbar_arrive(full_b(s)); if (++s == p.S) { s = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(full_b(s), 2u * (uint32_t)b_tile_bytes);
           tma_load_2d(dst, &tmapB, full_b(s), kb * BK, m0);
           tma_load_2d(dst + b_tile_bytes, &tmapB, full_b(s), kb * BK, p.Mpad + m0);
@@ -526,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     // single-lane branch the time per k-block did not depend on BN), so the 64-bit shared-memory descriptors are
     // kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
     // B200_TC_DEBUG bit 256 (timing experiment): issue every MMA with N = 16, whatever BN is
-    const uint32_t idesc = instr_desc_tf32((p.debug & 256) ? 16 : p.BN), idesc2 = instr_desc_tf32((p.debug & 256) ? 16 : 2 * p.BN);
+    const uint32_t idesc = instr_desc_tf32(TC_DBG(256) ? 16 : p.BN), idesc2 = instr_desc_tf32(TC_DBG(256) ? 16 : 2 * p.BN);
     const bool leader = elect_one();
     const uint32_t lo_first = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
     const uint32_t lo_step = (uint32_t)stage_bytes >> 4;
@@ -548,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         mbar_wait(full_a(sa), pha);  // A stage written to tensor memory by all 8 producer warps
         mbar_wait(full_b(s), ph);
         tc_fence_after();
-        if (leader && !(p.debug & 16)) {
+        if (leader && !TC_DBG(16)) {
           const uint32_t ah = tmem_base + (uint32_t)(a_col0 + sa * A_STAGE_COLS), al = ah + 32u;
           const uint32_t bh = lo;
           const int ksteps = (kb == p.nkb - 1) ? tail_ksteps : 4;
@@ -690,7 +712,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       const int row0 = p0 + quarter * 32;                 // first pixel of this warp's 32 rows
       const int rows_valid = min(32, p.P - row0);          // <= 0 for a quarter past the end
       const int mbase = m0 + g_begin * 16;
-      if (p.debug & 4) {
+      if (TC_DBG(4)) {
       } else if (fast_store) {
         // chunk columns in power-of-two blocks (16, 8 or 4 wide; 12 = 8 + 4): a lane keeps its chunk column and walks
         // down the rows, so an iteration is a bounds test, the swizzle, LDS.128, STG.128 and two pointer adds
@@ -911,7 +933,18 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   const size_t smem = (size_t)S * stage_bytes + (size_t)p.R * A_TILE_BYTES + fixed;
 
   p.vec_store = (a.ldy % 4 == 0 && (((uintptr_t)a.y) & 15) == 0) ? 1 : 0;
-  { static const int dbg = [] { const char* e = getenv("B200_TC_DEBUG"); return e ? atoi(e) : 0; }(); p.debug = dbg; }
+  {
+    static const int dbg = [] {
+      const char* e = getenv("B200_TC_DEBUG");
+      const int v = e ? atoi(e) : 0;
+      if (v && !B200_TC_DEBUG_MASKS) fprintf(stderr, "b200rt: B200_TC_DEBUG=%d ignored: this build has no role masks (make debug, B200RT_LIB=.../libb200rt_dbg.so)\n", v);
+      return v;
+    }();
+    p.debug = dbg;
+  }
+  p.m64Wo = a.Wo == 1 ? 0ull : ~0ull / (unsigned long long)a.Wo + 1ull;
+  p.m64Ho = a.Ho == 1 ? 0ull : ~0ull / (unsigned long long)a.Ho + 1ull;
+  p.nopad = (a.pt == 0 && a.pl == 0 && (long long)(a.Ho - 1) * a.sh + a.KH <= a.H && (long long)(a.Wo - 1) * a.sw + a.KW <= a.W) ? 1 : 0;
   p.magicC = a.C == 1 ? 0u : (uint32_t)(((1ull << 32) + a.C - 1) / a.C);
   p.magicKW = a.KW == 1 ? 0u : (uint32_t)(((1ull << 32) + a.KW - 1) / a.KW);
   p.magicWo = a.Wo == 1 ? 0u : (uint32_t)(((1ull << 32) + a.Wo - 1) / a.Wo);

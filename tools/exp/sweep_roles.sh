@@ -7,6 +7,6 @@ timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; ech
 timeout 60 tools/exp/build/tmem_layout > gpurun_out/tmem_layout.txt 2>&1; echo "tmem_layout rc=$?"
 for m in 0 1 2 32 34 35 39 16 4; do
   echo "== B200_TC_DEBUG=$m" >> gpurun_out/sweep.txt
-  B200_TC_DEBUG=$m timeout 300 python tools/tc_bench.py conv1 f2_e3 f4_e3 f8_e3 conv10 f8_sq f4_e1 >> gpurun_out/sweep.txt 2>&1
+  B200RT_LIB=$PWD/onnx_rusty_inference_engine_b200/lib/variants/libb200rt_dbg.so B200_TC_DEBUG=$m timeout 300 python tools/tc_bench.py conv1 f2_e3 f4_e3 f8_e3 conv10 f8_sq f4_e1 >> gpurun_out/sweep.txt 2>&1
 done
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json; cat gpurun_out/sweep.txt
