@@ -110,7 +110,7 @@ struct TcParams {
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
   int nopad;       // every tap of every output pixel lies inside the image: no validity masks (gather mode)
-  unsigned long long m64Wo, m64Ho;   // ceil(2^64 / d), 0 when d == 1: exact n / d for n < 2^32 by one multiply-high
+  unsigned long long m64Wo, m64Ho, m64NT;   // ceil(2^64 / d), 0 when d == 1: exact n / d for n < 2^32 by one multiply-high
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
 
@@ -291,6 +291,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   auto raw_full = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + r); };
   auto raw_empty = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + MAX_RAW + r); };
   const uint32_t ktab = (raw_empty(MAX_RAW) + 15u) & ~15u;   // gather mode: nkb x 8 entries {delta, r, s, valid mask}
+  // tile index -> (pixel tile, channel tile), one multiply-high instead of an integer division per tile and role
+  auto tile_pt = [&](int t) { const int tt = p.reverse ? p.total_tiles - 1 - t : t; return p.m64NT ? (int)__umul64hi((unsigned long long)tt, p.m64NT) : tt; };
+  auto tile_nt = [&](int t, int pt) { const int tt = p.reverse ? p.total_tiles - 1 - t : t; return tt - pt * p.n_tiles_n; };
   const int acc_cols = p.merged ? p.BN : 2 * p.BN;   // TMEM columns per accumulator stage
   const int a_col0 = p.nacc * acc_cols;   // first TMEM column of the A stages
 
@@ -416,14 +419,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       // (tap (0,0), channel 0) and two separable validity masks (bit 8*i+r: input row h0+r inside the image; bit
       // 8*i+s: column w0+s inside).  Per k-block the chunk's (r, s, offset) comes from the per-CTA table, shared by
       // all rows, so a load costs an add, a mask test and the LDG.
-      int l_tile = blockIdx.x, l_kb = kpar;   // load cursor
-      while (l_kb >= p.nkb) { l_kb -= p.nkb; l_tile += gridDim.x; }
+      // load cursor: the tile, and the ADDRESS of this thread's entry of the k-block's row of the decode table
+      // (128 bytes per k-block) instead of a k-block index -- the index would have to be combined with the thread's
+      // chunk for every lookup, and under the 72-register cap the compiler rebuilt the chunk from %tid each time
+      int l_tile = blockIdx.x;
+      uint32_t l_ent = ktab + 16u * (uint32_t)chunk + 128u * (uint32_t)kpar;
+      const uint32_t ktab_end = ktab + 128u * (uint32_t)p.nkb, ktab_bytes = 128u * (uint32_t)p.nkb;   // warp-uniform
+      while (l_ent >= ktab_end) { l_ent -= ktab_bytes; l_tile += gridDim.x; }
       int base[ROWS_PER_THREAD];              // element offsets from a.x (< 2^31, checked on the host)
       uint32_t hmask = 0, wmask = 0;
       auto set_tile = [&](int tile) {
         // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
         // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
-        const int p0 = ((p.reverse ? p.total_tiles - 1 - tile : tile) / p.n_tiles_n) * BM;
+        const int p0 = tile_pt(tile) * BM;
         const int t0 = p.m64Wo ? (int)__umul64hi((unsigned long long)p0, p.m64Wo) : p0, wo0 = p0 - t0 * a.Wo;
         const int n0 = p.m64Ho ? (int)__umul64hi((unsigned long long)t0, p.m64Ho) : t0, ho0 = t0 - n0 * a.Ho;
         hmask = 0; wmask = 0;
@@ -456,25 +464,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       float4 v[PREFETCH][ROWS_PER_THREAD];
       auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
         uint32_t delta, r, sx, vm;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(delta), "=r"(r), "=r"(sx), "=r"(vm) : "r"(ktab + 16u * (uint32_t)(l_kb * 8 + chunk)));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(delta), "=r"(r), "=r"(sx), "=r"(vm) : "r"(l_ent));
         if (p.nopad) {
-          // every tap is inside the image: four plain loads (vm = 0 only for the chunks past K in the last k-block)
+          // every tap is inside the image: four plain loads.  (The chunks past K in the last k-block have delta = 0:
+          // they re-read tap (0,0) and meet zero weights, exact for finite data like the fused Fire module's zeros.)
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vm && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+            if (TC_DBG(2)) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
           }
         } else {
           const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
+          const float* const xb = a.x + (int)delta;
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(xb + base[i]));
           }
         }
-        l_kb += NSETS;
-        if (l_kb >= p.nkb) {
-          do { l_kb -= p.nkb; l_tile += gridDim.x; } while (l_kb >= p.nkb);
+        l_ent += 128u * NSETS;
+        if (l_ent >= ktab_end) {
+          do { l_ent -= ktab_bytes; l_tile += gridDim.x; } while (l_ent >= ktab_end);
           if (l_tile < p.total_tiles) set_tile(l_tile);
         }
       };
@@ -513,7 +523,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int m0 = ((p.reverse ? p.total_tiles - 1 - t : t) % p.n_tiles_n) * p.BN;
+        const int m0 = tile_nt(t, tile_pt(t)) * p.BN;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(empty_b(s), ph ^ 1u);
           const uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
@@ -531,7 +541,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       int r = 0;
       uint32_t rph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int p0 = ((p.reverse ? p.total_tiles - 1 - t : t) / p.n_tiles_n) * BM;
+        const int p0 = tile_pt(t) * BM;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(raw_empty(r), rph ^ 1u);
           mbar_expect_tx(raw_full(r), (uint32_t)A_TILE_BYTES);
@@ -640,9 +650,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
       const int as = p.nacc == 2 ? (tc & 1) : 0;
       const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
-      const int tt = p.reverse ? p.total_tiles - 1 - t : t;
-      const int p0 = (tt / p.n_tiles_n) * BM;
-      const int m0 = (tt % p.n_tiles_n) * p.BN;
+      const int ptile = tile_pt(t);
+      const int p0 = ptile * BM;
+      const int m0 = tile_nt(t, ptile) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
       const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
@@ -942,6 +952,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
     }();
     p.debug = dbg;
   }
+  p.m64NT = p.n_tiles_n == 1 ? 0ull : ~0ull / (unsigned long long)p.n_tiles_n + 1ull;
   p.m64Wo = a.Wo == 1 ? 0ull : ~0ull / (unsigned long long)a.Wo + 1ull;
   p.m64Ho = a.Ho == 1 ? 0ull : ~0ull / (unsigned long long)a.Ho + 1ull;
   p.nopad = (a.pt == 0 && a.pl == 0 && (long long)(a.Ho - 1) * a.sh + a.KH <= a.H && (long long)(a.Wo - 1) * a.sw + a.KW <= a.W) ? 1 : 0;
