@@ -29,6 +29,8 @@
 //   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the weight tiles.
 //   warp 9      MMA issuer (uniform control flow, one elected lane, descriptors advanced by adds).
 //   warp 10     pointwise layers: TMA loads of raw fp32 A tiles into a shared-memory ring.
+//   warps 10-11 gather layers: per-tile row decode ({offset, validity masks} of the tile's 128 im2col rows) into
+//               shared-memory tables, one tile ahead of the producer set each of them serves.
 //   warps 12-27 A producers, two sets of 8 that take alternate k-blocks: warp w owns TMEM lanes 32*(w%4).. (hardware
 //               rule) and the 64-byte half ((w-12)/4)%2 of each k-block row.  Gather mode: im2col rows straight from
 //               the channels-last activation (any stride / padding / tap; (r, s, offset) of a chunk from a per-CTA
@@ -290,7 +292,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 4);
   auto raw_full = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + r); };
   auto raw_empty = [&](int r) { return bars + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + MAX_RAW + r); };
-  const uint32_t ktab = (raw_empty(MAX_RAW) + 15u) & ~15u;   // gather mode: nkb x 8 entries {delta, r, s, valid mask}
+  // gather mode: per producer set two row tables (128 rows x {element offset of tap (0,0) channel 0, validity masks}),
+  // written one tile ahead by the set's decode warp (ROWDEC_WARP0 + set), and their full / empty barriers
+  auto tab_full = [&](int set, int b) { return raw_empty(MAX_RAW) + 8u * (uint32_t)(set * 2 + b); };
+  auto tab_empty = [&](int set, int b) { return raw_empty(MAX_RAW) + 8u * (uint32_t)(4 + set * 2 + b); };
+  const uint32_t rowtab = (tab_empty(1, 1) + 8u + 15u) & ~15u;   // [set][buffer][128 rows] x 8 bytes
+  auto rowtab_of = [&](int set, int b) { return rowtab + 1024u * (uint32_t)(set * 2 + b); };
+  const uint32_t ktab = rowtab + 4096u;   // gather mode: nkb x 8 entries {delta, r, s, valid mask}
   // tile index -> (pixel tile, channel tile), one multiply-high instead of an integer division per tile and role
   auto tile_pt = [&](int t) { const int tt = p.reverse ? p.total_tiles - 1 - t : t; return p.m64NT ? (int)__umul64hi((unsigned long long)tt, p.m64NT) : tt; };
   auto tile_nt = [&](int t, int pt) { const int tt = p.reverse ? p.total_tiles - 1 - t : t; return tt - pt * p.n_tiles_n; };
@@ -329,6 +337,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       for (int s = 0; s < p.SA; ++s) { mbar_init(full_a(s), PROD_SET_WARPS); mbar_init(empty_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
       for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), PROD_SET_WARPS); }
+      for (int st = 0; st < 2; ++st)
+        for (int b = 0; b < 2; ++b) { mbar_init(tab_full(st, b), 1); mbar_init(tab_empty(st, b), PROD_SET_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -426,40 +436,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       uint32_t l_ent = ktab + 16u * (uint32_t)chunk + 128u * (uint32_t)kpar;
       const uint32_t ktab_end = ktab + 128u * (uint32_t)p.nkb, ktab_bytes = 128u * (uint32_t)p.nkb;   // warp-uniform
       while (l_ent >= ktab_end) { l_ent -= ktab_bytes; l_tile += gridDim.x; }
-      int base[ROWS_PER_THREAD];              // element offsets from a.x (< 2^31, checked on the host)
+      uint32_t base[ROWS_PER_THREAD];         // element offsets from a.x (< 2^31, checked on the host; int arithmetic)
       uint32_t hmask = 0, wmask = 0;
-      auto set_tile = [&](int tile) {
-        // first pixel of the tile -> (n, ho, wo) with two real divisions; the thread's rows follow with
-        // multiply-high divisions of small numbers (row < 128, so the carries stay below 2^16)
-        const int p0 = tile_pt(tile) * BM;
-        const int t0 = p.m64Wo ? (int)__umul64hi((unsigned long long)p0, p.m64Wo) : p0, wo0 = p0 - t0 * a.Wo;
-        const int n0 = p.m64Ho ? (int)__umul64hi((unsigned long long)t0, p.m64Ho) : t0, ho0 = t0 - n0 * a.Ho;
-        hmask = 0; wmask = 0;
-        const int last_row = p.P - 1 - p0;   // rows past the last pixel (last tile only)
+      // Per tile the thread needs, for its four rows, the element offset of tap (0,0) channel 0 and the validity
+      // masks.  They come from the set's row table in shared memory, filled one tile ahead by the set's decode warp
+      // (below): the decode is ~160 instructions for four rows, and with every producer warp doing it for itself it was
+      // a third of the producers' instructions on the short-reduction layers (conv1, fire2 / fire3).
+      uint32_t tcount = 0;   // tiles this set has entered: table buffer = tcount & 1, barrier phase = (tcount >> 1) & 1
+      auto set_tile = [&]() {
+        const uint32_t tb = tcount & 1u;
+        mbar_wait(tab_full(kpar, tb), (tcount >> 1) & 1u);
+        const uint32_t rt = rowtab_of(kpar, tb) + 8u * (uint32_t)(quarter * 32 + rsub);
+        uint32_t mk[ROWS_PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          int row = quarter * 32 + i * 8 + rsub;
-          const bool ok = row <= last_row;
-          if (p.nopad) row = min(row, last_row);   // no masks: a row past the end re-reads the last pixel (never stored)
-          const int wsum = wo0 + row;
-          const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
-          const int wo = wsum - cw * a.Wo;
-          const int hsum = ho0 + cw;
-          const int ch = p.magicHo ? (int)__umulhi((unsigned)hsum, p.magicHo) : hsum;   // hsum / Ho
-          const int ho = hsum - ch * a.Ho;
-          const int n = n0 + ch;
-          const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
-          base[i] = ((n * a.H + h0) * a.W + w0) * a.ldx;   // may be "negative" for padded taps: never dereferenced then
-          if (!p.nopad) {
-            // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
-            const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
-            const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
-            const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
-            const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
-            hmask |= hm << (8 * i);
-            wmask |= wm << (8 * i);
-          }
-        }
+        for (int i = 0; i < ROWS_PER_THREAD; ++i)
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(base[i]), "=r"(mk[i]) : "r"(rt + 64u * i) : "memory");
+        hmask = (mk[0] & 0xFFu) | ((mk[1] & 0xFFu) << 8) | ((mk[2] & 0xFFu) << 16) | (mk[3] << 24);
+        wmask = ((mk[0] >> 8) & 0xFFu) | (mk[1] & 0xFF00u) | ((mk[2] & 0xFF00u) << 8) | ((mk[3] & 0xFF00u) << 16);
+        // the buffer goes back to the decode warp only after the loads above have delivered (same device as raw_empty)
+        const uint32_t dep = (mk[0] ^ mk[1] ^ mk[2] ^ mk[3]) & p.zero;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tab_empty(kpar, tb) + dep);
+        ++tcount;
       };
       float4 v[PREFETCH][ROWS_PER_THREAD];
       auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
@@ -471,7 +469,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             if (TC_DBG(2)) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            else dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (base[i] + (int)delta)));
+            else dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (int)(base[i] + delta)));
           }
         } else {
           const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
@@ -479,17 +477,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(xb + base[i]));
+            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(xb + (int)base[i]));
           }
         }
         l_ent += 128u * NSETS;
         if (l_ent >= ktab_end) {
           do { l_ent -= ktab_bytes; l_tile += gridDim.x; } while (l_ent >= ktab_end);
-          if (l_tile < p.total_tiles) set_tile(l_tile);
+          if (l_tile < p.total_tiles) set_tile();
         }
       };
       const int my_items = (items - kpar + NSETS - 1) / NSETS;   // k-blocks this warp handles
-      if (my_items > 0) set_tile(l_tile);
+      if (my_items > 0) set_tile();
 #pragma unroll
       for (int d = 0; d < PREFETCH; ++d)
         if (d < my_items) issue(v[d]);
@@ -534,6 +532,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           if (++s == p.S) { s = 0; ph ^= 1u; }
         }
       }
+    }
+  } else if (!EPI16 && !p.a_tma && (warp == ATMA_WARP || warp == ATMA_WARP + 1)) {
+    // ================================================================ row decode for the gather producers
+    // Warp ATMA_WARP + set serves producer set `set`: for every tile the set enters, in the set's order, the 128 rows'
+    // {element offset of tap (0,0) channel 0 from a.x, validity masks} go to one of the set's two row tables.
+    // (With one k-block per tile the sets take alternate tiles; otherwise both enter every tile.)
+    const int set = warp - ATMA_WARP;
+    const int first = (p.nkb == 1) ? set : 0, step = (p.nkb == 1) ? NSETS : 1;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x + first * gridDim.x; tile < p.total_tiles; tile += step * gridDim.x, ++tcount) {
+      const uint32_t tb = tcount & 1u;
+      mbar_wait(tab_empty(set, tb), ((tcount >> 1) & 1u) ^ 1u);
+      // first pixel of the tile -> (n, ho, wo) with 64-bit multiply-highs; the rows follow with 32-bit multiply-high
+      // divisions of small numbers (row < 128, so the carries stay below 2^16)
+      const int p0 = tile_pt(tile) * BM;
+      const int t0 = p.m64Wo ? (int)__umul64hi((unsigned long long)p0, p.m64Wo) : p0, wo0 = p0 - t0 * a.Wo;
+      const int n0 = p.m64Ho ? (int)__umul64hi((unsigned long long)t0, p.m64Ho) : t0, ho0 = t0 - n0 * a.Ho;
+      const int last_row = p.P - 1 - p0;   // rows past the last pixel (last tile only)
+      const uint32_t tab = rowtab_of(set, tb);
+#pragma unroll 1
+      for (int i = 0; i < BM / 32; ++i) {
+        int row = i * 32 + lane;
+        const bool ok = row <= last_row;
+        const int rr = p.nopad ? min(row, last_row) : row;   // no masks: a row past the end re-reads the last pixel (never stored)
+        const int wsum = wo0 + rr;
+        const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
+        const int wo = wsum - cw * a.Wo;
+        const int hsum = ho0 + cw;
+        const int ch = p.magicHo ? (int)__umulhi((unsigned)hsum, p.magicHo) : hsum;   // hsum / Ho
+        const int ho = hsum - ch * a.Ho;
+        const int n = n0 + ch;
+        const int h0 = ho * a.sh - a.pt, w0 = wo * a.sw - a.pl;
+        const int rbase = ((n * a.H + h0) * a.W + w0) * a.ldx;   // may be "negative" for padded taps: never dereferenced then
+        // taps r with 0 <= h0 + r < H form the bit range [max(0,-h0), min(KH, H-h0)); same for s
+        const int rlo = max(0, -h0), rhi = min(a.KH, a.H - h0);
+        const int slo = max(0, -w0), shi = min(a.KW, a.W - w0);
+        const uint32_t hm = (ok && rhi > rlo) ? (((1u << rhi) - 1u) & ~((1u << rlo) - 1u)) : 0u;
+        const uint32_t wm = (shi > slo) ? (((1u << shi) - 1u) & ~((1u << slo) - 1u)) : 0u;
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tab + 8u * (uint32_t)row), "r"(rbase), "r"(hm | (wm << 8)) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tab_full(set, tb));
     }
   } else if (warp == ATMA_WARP) {
     // ================================================================ raw A tiles via TMA (pointwise layers only)
@@ -923,7 +963,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   const int n_epi = epi16 ? 16 : 8;
   const int groups_per_warp = ((p.BN >> 4) + n_epi / 4 - 1) / (n_epi / 4);
   p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
-  int fixed = 1024 + n_epi * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW) + 16;
+  int fixed = 1024 + n_epi * 32 * p.slab_pitch + 8 * p.Mpad + 8 * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 5 + 2 * MAX_RAW + 8) + 16 + 4096;   // ... barriers, row tables
   p.R = 0;
   if (!p.a_tma) fixed += 128 * p.nkb;   // gather mode: the per-CTA k decode table
   int S = (SMEM_MAX - fixed) / stage_bytes;

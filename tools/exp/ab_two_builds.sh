@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 240 python tools/tc_check.py > gpurun_out/tc_check.txt 2>&1; echo "tc_check rc=$?"; tail -2 gpurun_out/tc_check.txt
+timeout -s KILL 600 python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_models.py -x -q 2>&1 | tail -3
 H=$PWD/onnx_rusty_inference_engine_b200/lib/variants/libb200rt_head.so
 echo "== new" > gpurun_out/sweep29.txt
 timeout -s KILL 300 python tools/tc_bench.py conv1 f2_fused f4_e3 f6_e3 f8_e3 f2_sq f8_sq f4_e1 conv10 >> gpurun_out/sweep29.txt 2>&1
