@@ -305,7 +305,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   const int acc_cols = p.merged ? p.BN : 2 * p.BN;   // TMEM columns per accumulator stage
   const int a_col0 = p.nacc * acc_cols;   // first TMEM column of the A stages
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle from lane 0: the compiler then knows it is warp-uniform and keeps everything derived
+  // from it (role branches, TMEM addresses, barrier addresses) in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // per-channel epilogue constants -> shared memory once per CTA (the epilogue then needs no global loads)
   for (int m = threadIdx.x; m < p.Mpad; m += NTHREADS) {
@@ -349,6 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // uniform for the compiler as well
 
   if (warp >= PROD_WARP0) {
     // ================================================================ A producers (16 warps, two sets of 8)
@@ -473,11 +476,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           }
         } else {
           const uint32_t m = (hmask >> r) & (wmask >> sx) & vm;   // bit 8*i: row i valid for this tap
-          const float* const xb = a.x + (int)delta;
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(xb + (int)base[i]));
+            if (((m >> (8 * i)) & 1u) && !TC_DBG(2)) dst[i] = __ldg(reinterpret_cast<const float4*>(a.x + (int)(base[i] + delta)));
           }
         }
         l_ent += 128u * NSETS;
