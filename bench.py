@@ -161,7 +161,19 @@ def run_own(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries ONE JSON line: whatever NCCL prints on fd 1 while the communicator is created (the pool's
+        # NCCL_DEBUG setting makes it print "NCCL version ...") is sent to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B, K, W = args.batch, args.steps, max(3, args.warmup)
 
     if rank == 0:
