@@ -1,11 +1,14 @@
 // tcgen05 3xTF32 implicit-GEMM convolution for sm_100a -- persistent, warp-specialised, A operand in tensor memory.
 //
 // Semantics: conv2d, convolution_op.rs:224-517 (+ folded Add add_op.rs:75 and Relu relu_op.rs:31-33), identical to
-// conv_simt.cu.  fp32 accuracy is kept by splitting every operand x into hi = rna_tf32(x) and lo = rna_tf32(x - hi)
-// and issuing three tensor-core products per k-step: hi*hi into a main accumulator, lo*hi + hi*lo into a separate
-// correction accumulator (the tensor core truncates when it folds products into the fp32 accumulator; keeping the
-// 2^-11-times smaller terms apart costs no extra MMAs and removes two thirds of the truncation steps from the main
-// sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.
+// conv_simt.cu.  fp32 accuracy is kept by splitting every operand x into hi + lo (weights: hi = rna_tf32(x),
+// lo = rna_tf32(x - hi), once per model; activations: hi = x truncated to TF32, lo = x - hi, 2 instructions per element
+// in the producers) and issuing three tensor-core products per k-step: hi*hi into a main accumulator, lo*hi + hi*lo
+// into a separate correction accumulator (the tensor core truncates when it folds products into the fp32 accumulator;
+// keeping the 2^-11-times smaller terms apart costs no extra MMAs and removes two thirds of the truncation steps from
+// the main sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.  Short
+// reductions on wide tiles (BN > 64, K <= 288) use ONE merged accumulator instead, so that two accumulator stages fit
+// (launch_conv_tc, MERGED_MAX_K).
 //
 // GEMM view: D[P x M] = A[P x K] * W[M x K]^T, P = N*Ho*Wo output pixels, K = KH*KW*C ordered (r, s, c).
 //   UMMA tile 128 pixels (TMEM lanes) x BN <= 128 output channels (TMEM columns), k-block = 32 floats = 4 k-steps of
@@ -17,9 +20,9 @@
 //     puts float 4c+e of a 16-float group in TMEM column 2c+e (e < 2) or 8+2c+e-2 (e >= 2), so the weight
 //     preparation applies the same permutation to K inside every group of 16 (a contraction does not care).
 //   TMEM columns (512): [accumulator stages: {main | correction} x BN each][A stages: {hi 32 | lo 32} each].
-//     BN <= 64: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1) + four A stages;
-//     BN  > 64: one accumulator stage, four A stages; the epilogue drains TMEM to a shared-memory slab first and
-//     releases the accumulator before it touches global memory.
+//     BN <= 64, or merged accumulator: two accumulator stages (the epilogue of tile i overlaps the main loop of tile
+//     i+1) + four A stages;  otherwise one accumulator stage, four A stages; the epilogue drains TMEM to a
+//     shared-memory slab first and releases the accumulator before it touches global memory.
 // One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 28 warps in one of two role
 // layouts (struct Roles); the default one:
 //   warps 0-7   epilogue: warps w, w+4 share TMEM lanes 32*(w%4).. and take the two halves of the tile's channels.
