@@ -96,6 +96,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def workload_name(batch: int) -> str:
+    return (f"SqueezeNet1.0-8 (seeded synthetic weights) batch {batch} per GPU, 3x224x224 fp32 "
+            "N(0,10^2) (BASELINE.json configs[2])")
+
+
 def cpu_reference_rate(images: int, threads: int, seed: int = 11):
     """Oracle (CPU restatement of the reference algorithm) on `images` synthetic images with `threads` host threads."""
     import numpy as np
@@ -131,7 +136,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SqueezeNet1.0-8 synthetic 3x224x224 fp32, batch 256 (configs[2])",
+        "config": {"workload": workload_name(args.batch),   # the same workload string as the GPU arm's line
+                   "global_batch": args.gpus * args.batch,
                    "sample": f"{per_step} images per step (1 per host thread), batch-1 reference runs"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{n_total} images, {threads} threads; C restatement of the reference algorithm "
@@ -319,8 +325,7 @@ def run_own(args):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"SqueezeNet1.0-8 (seeded synthetic weights) batch {B} per GPU, 3x224x224 fp32 "
-                                   "N(0,10^2) (BASELINE.json configs[2])",
+            "config": {"workload": workload_name(B),
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, replicated weights",
                        "l2": "inputs (154 MB per batch, two alternating) and activations exceed the 126 MB L2",
                        "conv_path": args.conv_path},

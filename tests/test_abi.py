@@ -96,3 +96,28 @@ def test_reference_panics_become_error_codes():
     pp.auto_pad = 3
     assert L.lib().b200_maxpool2d_out_dims(L._i64arr((1, 4, 54, 54)), C.byref(pp), y) == 0
     assert tuple(y) == (1, 4, 27, 27)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): one JSON line on stdout with the
+    contract's keys and the GPU arm's metric / unit / workload; under torchrun only rank 0 works and prints."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "SqueezeNet1.0 images/sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "batch 256" in d["config"]["workload"] and "model" not in d["config"]
+    env2 = dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, env=env2, cwd=root, timeout=120)
+    assert r2.returncode == 0 and r2.stdout.strip() == "", (r2.returncode, r2.stdout, r2.stderr[-500:])
