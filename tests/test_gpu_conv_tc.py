@@ -33,6 +33,10 @@ CASES = [
     (3, 64, 13, 13, 256, 3, 1, 1),         # fire8-like: two channel tiles of 128, 18 k-blocks
     (1, 32, 40, 40, 128, 3, 2, 1),         # strided 3x3 with padding
     (40, 32, 54, 54, 128, 1, 1, 0),        # 912 tiles > 148 CTAs: several tiles per persistent CTA
+    # gather mode with several tiles per CTA: the row-decode warps run ahead of the two producer sets
+    (24, 16, 90, 90, 32, 1, 2, 0),         # 1x1 stride 2: ONE k-block per tile, so the sets take alternate tiles (380 tiles)
+    (30, 8, 33, 33, 64, 3, 1, 1),          # three k-blocks (odd): a set's k-blocks alternate position from tile to tile
+    (26, 4, 30, 30, 16, 3, 1, 0),          # no padding (mask-free path), two k-blocks, BN = 16, 160 tiles
 ]
 
 
