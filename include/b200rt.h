@@ -70,6 +70,9 @@ int b200_device_count(void);
 int b200_ctx_create(int device, void *stream, b200_ctx **out);
 int b200_ctx_destroy(b200_ctx *ctx);
 int b200_sync(b200_ctx *ctx);
+/* The context's cudaStream_t as void* (its own, or the one passed to b200_ctx_create): lets a host that already owns
+ * CUDA work order it against the backend's with events. */
+void *b200_ctx_stream(const b200_ctx *ctx);
 /* Number of backend kernels launched on this context since creation (CUDA-graph replays count the
  * kernels inside the graph). */
 int64_t b200_ctx_launch_count(const b200_ctx *ctx);
@@ -157,6 +160,12 @@ int b200_model_run(b200_model *m, const float *host_in, int64_t batch, float *ho
  * be pinned and must stay valid until b200_model_sync returns. */
 int b200_model_run_async(b200_model *m, const float *host_in, int64_t batch, float *host_out);
 int b200_model_sync(b200_model *m);
+/* Multi-GPU inference() (model_inference.rs:29 has no counterpart: the reference is single-device): models[i] holds the
+ * same ONNX graph on its own context (one context per device).  The batch is split contiguously -- the first
+ * batch % n shards get one image more -- each shard goes through b200_model_run_async of its model on its own host
+ * thread, and host_out receives the [batch, out_per_image] logits in shard (= image) order.  Weights are replicated;
+ * there is no collective on the data path.  Returns the first failing shard's code. */
+int b200_model_run_sharded(b200_model *const *models, int n, const float *host_in, int64_t batch, float *host_out);
 /* Device-resident: d_in / d_out are device pointers (NCHW dense input, [batch, out_per_image] output)
  * on the context's device; asynchronous on the context's stream. */
 int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float *d_out);

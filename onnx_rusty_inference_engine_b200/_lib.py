@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200_ctx_destroy": (C.c_int, [_vp]),
     "b200_sync": (C.c_int, [_vp]),
     "b200_ctx_launch_count": (C.c_int64, [_vp]),
+    "b200_ctx_stream": (_vp, [_vp]),
     "b200_tensor_alloc": (C.c_int, [_vp, _i64p, C.c_int, C.POINTER(_vp)]),
     "b200_tensor_upload": (C.c_int, [_vp, _vp, C.c_size_t]),
     "b200_tensor_download": (C.c_int, [_vp, _vp, C.c_size_t]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "b200_model_run_device": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "b200_model_run_async": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "b200_model_sync": (C.c_int, [_vp]),
+    "b200_model_run_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int64, _vp]),
     "b200_model_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "b200_model_profile": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "b200_model_launches_per_run": (C.c_int64, [_vp, C.c_int64]),
@@ -126,6 +128,11 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().b200_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        """The context's cudaStream_t as an integer (0 = the legacy default stream)."""
+        return int(lib().b200_ctx_stream(self._h) or 0)
 
     def close(self) -> None:
         if self._h:
@@ -337,3 +344,14 @@ class Model:
         if self._h:
             lib().b200_model_free(self._h)
             self._h = _vp()
+
+
+def run_sharded(models: Sequence["Model"], x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """b200_model_run_sharded: x [N,C,H,W] split contiguously over `models` (one per device), logits in image order."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.shape[0]
+    if out is None:
+        out = np.empty((n, models[0].out_per_image), dtype=np.float32)
+    arr = (_vp * len(models))(*[m._h for m in models])
+    check(lib().b200_model_run_sharded(arr, len(models), x.ctypes.data_as(_vp), n, out.ctypes.data_as(_vp)))
+    return out

@@ -99,6 +99,7 @@ static int new_tensor(b200_ctx* ctx, const int64_t* dims, int rank, b200_tensor*
   const size_t bytes = (size_t)t->v.pixels() * t->v.ld * sizeof(float);
   B200_TRY(alloc_storage(ctx, bytes, &t->storage));
   t->v.p = (float*)t->storage.get();
+  ctx_retain(ctx);
   *out = t.release();
   return 0;
 }
@@ -112,6 +113,8 @@ static int ensure_out(b200_ctx* ctx, b200_tensor** y, const int64_t* dims, int r
     if ((*y)->dims[i] != dims[i])
       B200_FAIL(B200_EINVAL, "output dim %d is %lld, expected %lld", i, (long long)(*y)->dims[i], (long long)dims[i]);
   (*y)->pad_zeroed = false;
+  (*y)->tc.reset();   // about to be overwritten: a cached weight preparation of the old contents is stale
+  (*y)->version++;
   return 0;
 }
 
@@ -128,6 +131,19 @@ struct Guard {
     c->mu.unlock();
   }
 };
+
+void ctx_retain(b200_ctx* c) { c->refs.fetch_add(1, std::memory_order_relaxed); }
+void ctx_release(b200_ctx* c) {
+  if (c->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->l2_flush) cudaFree(c->l2_flush);
+  if (c->owns_stream) cudaStreamDestroy(c->stream);
+  if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+  delete c;
+}
 
 int conv_effective_channels(const b200_tensor* x, const b200_tensor* w) {
   const int C = x->v.C;
@@ -184,13 +200,22 @@ int b200_ctx_create(int device, void* stream, b200_ctx** out) {
 
 int b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return 0;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->l2_flush) cudaFree(ctx->l2_flush);
-  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  {
+    // in-flight calls from other threads hold the lock; wait for them, then drain the stream
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (ctx->closed) B200_FAIL(B200_EINVAL, "context destroyed twice");
+    ctx->closed = true;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+  }
+  ctx_release(ctx);   // tensors / models still alive keep the context until they are freed
   return 0;
 }
+
+void* b200_ctx_stream(const b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int b200_sync(b200_ctx* ctx) {
   if (!ctx) B200_FAIL(B200_EINVAL, "ctx is NULL");
@@ -220,7 +245,7 @@ int b200_tensor_upload(b200_tensor* t, const float* host, size_t n) {
   if (v.dense() && (t->rank != 4 || v.H * v.W == 1 || v.C == 1)) {
     B200_CUDA(cudaMemcpyAsync(v.p, host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    t->pad_zeroed = true;
+    t->pad_zeroed = !t->is_view;
     return 0;
   }
   float* stage = nullptr;
@@ -228,13 +253,15 @@ int b200_tensor_upload(b200_tensor* t, const float* host, size_t n) {
   cudaError_t e = cudaMemcpyAsync(stage, host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
   int rc = 0;
   if (e == cudaSuccess) {
-    rc = launch_nchw_to_rows(stage, v, /*zero_pad_lanes=*/true, ctx->stream);
+    // A tensor that owns its rows zero-fills the lanes [C, ld) (the padded 4th lane of a C = 3 input).  A channel
+    // view writes exactly its C lanes: [C, ld) of its pitch are the siblings' channels.
+    rc = launch_nchw_to_rows(stage, v, /*zero_pad_lanes=*/!t->is_view, ctx->stream);
     ctx->launches++;
     e = cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(stage);
   if (e != cudaSuccess) B200_FAIL(B200_ECUDA, "upload failed: %s", cudaGetErrorString(e));
-  if (rc == 0) t->pad_zeroed = true;
+  if (rc == 0) t->pad_zeroed = !t->is_view;
   return rc;
 }
 
@@ -281,14 +308,20 @@ int b200_tensor_view_channels(b200_tensor* parent, int64_t c_off, int64_t c_len,
   t->v.C = (int)c_len;
   t->v.p = parent->v.p + c_off;
   t->storage = parent->storage;
+  t->is_view = true;
+  ctx_retain(t->ctx);
   *out = t.release();
   return 0;
 }
 
 int b200_tensor_free(b200_tensor* t) {
   if (!t) return 0;
-  Guard g(t->ctx);
-  delete t;
+  b200_ctx* ctx = t->ctx;
+  {
+    Guard g(ctx);
+    delete t;
+  }
+  ctx_release(ctx);
   return 0;
 }
 
@@ -427,19 +460,30 @@ int b200_matmul(b200_ctx* ctx, const b200_tensor* a, const b200_tensor* b, const
   Guard gd(ctx);
   int64_t yd[2] = {R, N};
   B200_TRY(ensure_out(ctx, y, yd, 2));
-  // B^T [N][K] so that both operands are K-contiguous; the GEMM is a 1x1 "convolution" over R pixels.
-  float* bt = nullptr;
-  B200_CUDA(cudaMallocAsync((void**)&bt, (size_t)N * K * sizeof(float) + 16, ctx->stream));
-  int rc = launch_transpose2d(b->v.p, K, N, bt, ctx->stream);
+  // B^T [N][K] so that both operands are K-contiguous; the GEMM is a pointwise "convolution" over R pixels on the
+  // convolution's tcgen05 path (TMA-fed A tiles, one channel tile of N columns).  The split / permuted weight tiles are
+  // cached on b (a rank-2 tensor is never a Conv weight) and rebuilt when b is uploaded again.
   ConvArgs c{};
   c.x = a->v.p; c.N = R; c.C = K; c.H = 1; c.W = 1; c.ldx = a->v.ld;
-  c.w = bt; c.M = N; c.KH = 1; c.KW = 1; c.K = K; c.ldw = K; c.wc = K;
+  c.w = nullptr; c.M = N; c.KH = 1; c.KW = 1; c.K = K; c.ldw = K; c.wc = K;
   c.bias = bias ? bias->v.p : nullptr; c.chan_add = nullptr;
   c.y = (*y)->v.p; c.Ho = 1; c.Wo = 1; c.ldy = (*y)->v.ld;
   c.sh = c.sw = 1; c.pt = c.pl = 0; c.relu = 0;
-  if (rc == 0) rc = launch_conv_simt(c, ctx->stream);
-  cudaFreeAsync(bt, ctx->stream);
-  ctx->launches += 2;
+  static const int forced_path = [] { const char* e = getenv("B200_CONV_PATH"); return e ? atoi(e) : 0; }();
+  const bool use_tc = forced_path != 1 && tc_supported(c) == 0;
+  b200_tensor* bm = const_cast<b200_tensor*>(b);
+  int rc = 0;
+  if (!use_tc || !bm->tc) {
+    float* bt = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&bt, (size_t)N * K * sizeof(float) + 16, ctx->stream));
+    rc = launch_transpose2d(b->v.p, K, N, bt, ctx->stream);
+    ctx->launches++;
+    c.w = bt;
+    if (rc == 0 && use_tc) { rc = tc_prepare_weights(bt, N, K, ctx->stream, &bm->tc); ctx->launches++; }
+    if (rc == 0 && !use_tc) { rc = launch_conv_simt(c, ctx->stream); ctx->launches++; }
+    cudaFreeAsync(bt, ctx->stream);
+  }
+  if (rc == 0 && use_tc) { rc = launch_conv_tc(c, *bm->tc, ctx->stream); ctx->launches++; }
   return rc;
 }
 
@@ -463,6 +507,7 @@ int b200_reshape(b200_ctx* ctx, const b200_tensor* x, const int64_t* shape, int 
     t->ctx = ctx; t->rank = 2; t->dims[0] = d[0]; t->dims[1] = d[1];
     t->v.p = v.p; t->v.N = (int)d[0]; t->v.C = (int)d[1]; t->v.H = t->v.W = 1; t->v.ld = (int)d[1];
     t->storage = x->storage;  // zero-copy alias
+    ctx_retain(ctx);
     *y = t.release();
     return 0;
   }
@@ -501,6 +546,7 @@ int b200_dropout(b200_ctx* ctx, const b200_tensor* x, float ratio, b200_tensor**
   if (*y == nullptr) {
     std::unique_ptr<b200_tensor> t(new b200_tensor(*x));  // alias: shares storage
     t->tc.reset();
+    ctx_retain(ctx);
     *y = t.release();
     return 0;
   }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -115,7 +116,15 @@ struct b200_ctx {
   int64_t launches = 0;
   int sm_count = 0;
   float* l2_flush = nullptr;  // lazily allocated 256 MiB scratch for profile runs
+  // Tensors and models keep their context alive: b200_ctx_destroy only marks the context closed and drops the
+  // caller's reference; the CUDA resources go when the last handle created on it is freed.
+  std::atomic<int> refs{1};
+  bool closed = false;
 };
+namespace b200 {
+void ctx_retain(b200_ctx* c);
+void ctx_release(b200_ctx* c);   // frees the context when the last reference goes
+}
 
 struct b200_tensor {
   b200_ctx* ctx = nullptr;
@@ -123,7 +132,8 @@ struct b200_tensor {
   int64_t dims[4] = {0, 0, 0, 0};
   b200::TView v;                       // physical view
   std::shared_ptr<void> storage;       // owning allocation (shared with views / aliases)
-  bool pad_zeroed = false;             // lanes [C, ld) are known to be zero (set by upload)
+  bool pad_zeroed = false;             // lanes [C, ld) are known to be zero (set by upload; never for views)
+  bool is_view = false;                // channel view of a wider tensor: lanes [C, ld) belong to the siblings
   std::shared_ptr<b200::TcWeights> tc; // cached tcgen05 weight preparation (when used as Conv weights)
   uint64_t version = 0;                // bumped by upload; invalidates `tc`
 };

@@ -19,6 +19,7 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <thread>
 
 #include "internal.h"
 #include "onnx_wire.h"
@@ -146,7 +147,13 @@ int upload_const(b200_model* m, const std::string& key, const std::vector<float>
   std::unique_ptr<DevBuf> b(new DevBuf());
   b->bytes = std::max<size_t>(host.size() * sizeof(float), 16);
   if (cudaMalloc((void**)&b->p, b->bytes) != cudaSuccess) B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for constant %s", b->bytes, key.c_str());
-  if (!host.empty()) B200_CUDA(cudaMemcpy(b->p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // on the context's stream (the consumers -- the weight-split kernel, the plan's launches -- run there; the legacy
+  // stream a plain cudaMemcpy uses is not ordered against a non-blocking stream), then wait: `host` is pageable and
+  // may be freed by the caller
+  if (!host.empty()) {
+    B200_CUDA(cudaMemcpyAsync(b->p, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  }
   *out = b->p;
   m->consts[key] = std::move(b);
   return 0;
@@ -750,8 +757,25 @@ int Planner::do_matmul(size_t i) {
   c.bias = dbias; c.chan_add = nullptr;
   c.y = y.v.p; c.Ho = 1; c.Wo = 1; c.ldy = y.v.ld; c.sh = c.sw = 1; c.pt = c.pl = 0; c.relu = 0;
   const double R = (double)a->dims[0];
-  add_step(label, "matmul_simt", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
-           [c](cudaStream_t st) { return launch_conv_simt(c, st); });
+  c.reverse = next_reverse();
+  // mul_op.rs:23 on the convolution's tcgen05 path: rows are the "pixels" of a pointwise layer (TMA-fed A tiles), the
+  // N columns one channel tile (MNIST: 10 -> BN = 16)
+  if (m->opt_conv_path != 1 && tc_supported(c) == 0) {
+    std::shared_ptr<TcWeights> tcw;
+    if (!dry) {
+      auto it = m->tc_weights.find("tc:" + key);
+      if (it == m->tc_weights.end()) {
+        B200_TRY(tc_prepare_weights(dw, N, K, m->ctx->stream, &tcw));
+        m->tc_weights["tc:" + key] = tcw;
+      } else tcw = it->second;
+    }
+    add_step(label, "matmul_tc", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
+             [c, tcw](cudaStream_t st) { return launch_conv_tc(c, *tcw, st); });
+  } else {
+    if (m->opt_conv_path == 2) B200_FAIL(B200_EUNSUPPORTED, "MatMul %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
+    add_step(label, "matmul_simt", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
+             [c](cudaStream_t st) { return launch_conv_simt(c, st); });
+  }
   env[out_name] = y;
   return 0;
 }
@@ -916,7 +940,9 @@ int Planner::run() {
       bool ok = shp.count(n.input[0]) && shp.count(n.input[1]) && shp.count(n.output[0]);
       if (ok) {
         auto a = shp[n.input[0]], b = shp[n.input[1]];
-        ok = a[0] == b[0] && a[2] == b[2] && a[3] == b[3];
+        // a slice that does not start on a 16-byte boundary would push its producer to scalar stores and make its
+        // consumer ineligible for the TMA / 128-bit gather paths: such a Concat is copied instead
+        ok = a[0] == b[0] && a[2] == b[2] && a[3] == b[3] && a[1] % 4 == 0;
         if (ok) {
           redirect[n.input[1]].second = (int)a[1];
           Val parent; parent.rank = 4;
@@ -1076,6 +1102,7 @@ int b200_model_load_onnx(b200_ctx* ctx, const uint8_t* bytes, size_t len, b200_m
   Plan* p = nullptr;
   B200_TRY(build_plan(m.get(), 1, &p));  // validates every node up front (unknown op / attribute errors surface here)
   m->out_per_image = p->out_per_image;
+  ctx_retain(ctx);
   *out = m.release();
   return 0;
 }
@@ -1090,9 +1117,15 @@ int b200_model_load_file(b200_ctx* ctx, const char* path, b200_model** out) {
 
 int b200_model_free(b200_model* m) {
   if (!m) return 0;
-  Guard g(m->ctx);
-  cudaStreamSynchronize(m->ctx->stream);
-  delete m;
+  b200_ctx* ctx = m->ctx;
+  {
+    Guard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (m->h2d) cudaStreamSynchronize(m->h2d);
+    if (m->d2h) cudaStreamSynchronize(m->d2h);
+    delete m;
+  }
+  ctx_release(ctx);
   return 0;
 }
 
@@ -1218,6 +1251,43 @@ int b200_model_sync(b200_model* m) {
   B200_CUDA(cudaStreamSynchronize(m->ctx->stream));
   if (m->h2d) B200_CUDA(cudaStreamSynchronize(m->h2d));
   if (m->d2h) B200_CUDA(cudaStreamSynchronize(m->d2h));
+  return 0;
+}
+
+// inference() over several GPUs of one box: images are independent units on this path, so the
+// batch is split contiguously (the first batch % n shards get one extra image), every shard runs through the pipelined
+// host-to-host entry of its own model / context / device on its own host thread, and the logits land in host_out in
+// shard order.  No data-path collective and no dependency on torch or NCCL: the only exchange is each device's D2H copy
+// of its logits rows into the caller's buffer.
+int b200_model_run_sharded(b200_model* const* models, int n, const float* host_in, int64_t batch, float* host_out) {
+  if (!models || n <= 0 || !host_in || !host_out) B200_FAIL(B200_EINVAL, "NULL / empty argument");
+  if (batch < 0) B200_FAIL(B200_EINVAL, "batch must be non-negative");
+  for (int i = 0; i < n; ++i) {
+    if (!models[i]) B200_FAIL(B200_EINVAL, "models[%d] is NULL", i);
+    for (int k = 1; k < 4; ++k)
+      if (models[i]->in_dims[k] != models[0]->in_dims[k]) B200_FAIL(B200_EINVAL, "models[%d] has a different input shape", i);
+    if (models[i]->out_per_image != models[0]->out_per_image) B200_FAIL(B200_EINVAL, "models[%d] has a different output size", i);
+    for (int j = 0; j < i; ++j)
+      if (models[j]->ctx == models[i]->ctx) B200_FAIL(B200_EINVAL, "models[%d] and models[%d] share a context: one context per shard", j, i);
+  }
+  const int64_t in_per = models[0]->in_dims[0] * models[0]->in_dims[1] * models[0]->in_dims[2] * models[0]->in_dims[3];
+  const int64_t out_per = models[0]->out_per_image;
+  const int64_t base = batch / n, rem = batch % n;
+  std::vector<int> rcs((size_t)n, 0);
+  std::vector<std::string> errs((size_t)n);
+  auto shard = [&](int i) {
+    const int64_t lo = i * base + std::min<int64_t>(i, rem), cnt = base + (i < rem ? 1 : 0);
+    if (cnt == 0) return;
+    int rc = b200_model_run_async(models[i], host_in + lo * in_per, cnt, host_out + lo * out_per);
+    if (rc == 0) rc = b200_model_sync(models[i]);
+    if (rc) { rcs[(size_t)i] = rc; errs[(size_t)i] = b200_last_error(); }   // the message is thread-local: carry it over
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n; ++i) th.emplace_back(shard, i);
+  shard(0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i)
+    if (rcs[(size_t)i]) B200_FAIL(rcs[(size_t)i], "shard %d of %d: %s", i, n, errs[(size_t)i].c_str());
   return 0;
 }
 

@@ -113,13 +113,26 @@ class Engine:
 
     def run_torch(self, x, out=None):
         """x: contiguous float32 CUDA tensor [N,C,H,W] on this engine's device; returns [N, out_per_image].
-        Asynchronous on the engine's stream (pass torch's current stream at construction to stay ordered)."""
+        Ordered against torch: when the engine's stream is not torch's current stream, the engine's stream first waits
+        for what torch has enqueued (x is ready), and torch's current stream then waits for the run (out is ready for
+        the next torch op or NCCL collective); both tensors are marked as used on the engine's stream so the caching
+        allocator does not hand their memory out early.  With the same stream on both sides this is plain stream order."""
         import torch
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         n = x.shape[0]
         if out is None:
             out = torch.empty((n, self.out_per_image), dtype=torch.float32, device=x.device)
+        cur = torch.cuda.current_stream(x.device)
+        mine = self.ctx.stream
+        if cur.cuda_stream == mine:
+            self.model.run_raw(x.data_ptr(), n, out.data_ptr(), device=True)
+            return out
+        es = torch.cuda.ExternalStream(mine, device=x.device)
+        es.wait_stream(cur)
         self.model.run_raw(x.data_ptr(), n, out.data_ptr(), device=True)
+        cur.wait_stream(es)
+        x.record_stream(es)
+        out.record_stream(es)
         return out
 
     def run_pinned_async(self, x_host, out_host) -> None:

@@ -39,6 +39,17 @@ def test_no_cpu_fallback():
         Engine(os.path.join(ROOT, "tests", "golden", "mnist-8.onnx"))
 
 
+def test_run_sharded_error_paths_without_a_gpu():
+    """b200_model_run_sharded validates its arguments before touching a device (no compute without a GPU)."""
+    lib = L.lib()
+    x = np.zeros((4,), np.float32); y = np.zeros((4,), np.float32)
+    assert lib.b200_model_run_sharded(None, 0, x.ctypes.data_as(C.c_void_p), 1, y.ctypes.data_as(C.c_void_p)) == -1
+    arr = (C.c_void_p * 1)(None)
+    assert lib.b200_model_run_sharded(arr, 1, x.ctypes.data_as(C.c_void_p), 1, y.ctypes.data_as(C.c_void_p)) == -1
+    assert b"models[0] is NULL" in lib.b200_last_error()
+    assert lib.b200_ctx_stream(None) is None
+
+
 def _conv_dims(x, w, strides, pads, auto_pad):
     p = L.ConvParams(L._i64arr(strides, 2), L._i64arr(pads, 4), L._i64arr((0, 0), 2), 0, auto_pad, 0)
     y = (C.c_int64 * 4)()

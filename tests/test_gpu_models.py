@@ -54,6 +54,20 @@ def test_group17_entry_point(capsys):
     assert "Expected Data:" in out                                       # main.rs:41
 
 
+def test_cli_binaries_mirror_main_rs():
+    """main.rs:9-53 as a compiled binary over the C ABI and as `python -m`: the reference's result lines, exit 0 on a match."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    args = [MNIST_ONNX, os.path.join(GOLDEN, "mnist_data_0.pb"), os.path.join(GOLDEN, "mnist_output_0.pb"), "Input3", "Parameter193"]
+    exe = os.path.join(ROOT, "onnx_rusty_inference_engine_b200", "lib", "onnx_rusty_inference_engine_bin")
+    for cmd in ([exe] + args, [sys.executable, "-m", "onnx_rusty_inference_engine_b200"] + args):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert "MNist-8 Inference results: Class 3-nth predicted." in r.stdout
+        assert "Expected Data:" in r.stdout and "Match (1e-4 rel + 1e-5 abs, argmax): yes" in r.stdout
+
+
 def test_mnist_batch_vs_oracle(ctx):
     """Config 5 at test size: batch 64 of N(0,10^2) images == 64 batch-1 oracle runs; batch-position invariant."""
     from onnx_rusty_inference_engine_b200 import synth
@@ -184,6 +198,24 @@ def test_squeezenet_batch_properties(ctx, synth_onnx):
     assert np.isfinite(big).all() and (big >= 0).all()
     for _ in range(6):                               # run-to-run determinism at full size
         assert np.array_equal(eng(np.tile(xs, (32, 1, 1, 1))), big)
+
+
+def test_squeezenet_batch256_sampled_vs_oracle(ctx, synth_onnx):
+    """Config 3 as SURVEY.md section 8(d) states it: the batch-256 run itself (seed 1, N(0,10^2)), >= 8 images sampled FROM
+    ITS OUTPUT -- spread over the persistent CTAs' tile schedules: first, last, both sides of the 148-SM boundary --
+    against the oracle, north_star tolerance and identical argmax."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(256, seed=1)
+    eng = Engine(synth_onnx, ctx=ctx)
+    got = eng(xs)
+    assert got.shape == (256, 1000)
+    idx = [0, 37, 100, 148, 149, 200, 254, 255]
+    want = rm.run_batch(ow.load_model(synth_onnx), xs[idx], threads=8)
+    assert_close(got[idx], want, "squeezenet batch 256, sampled images vs oracle")
+    assert (got[idx].argmax(1) == want.argmax(1)).all()
+    assert np.allclose(got.sum(1), 1.0, atol=1e-5) and np.isfinite(got).all()
 
 
 def test_engine_on_torch_stream(synth_onnx):

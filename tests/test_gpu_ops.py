@@ -170,7 +170,9 @@ def test_matmul(ctx):
     from oracle import ref_ops as R
     import ctypes
     rng = np.random.default_rng(5)
-    for (r, k, n) in [(1, 256, 10), (7, 256, 10), (3, 4, 3), (130, 37, 65)]:
+    # (r, 256, 10): MNIST's Times212 -- tcgen05 path (rows as pixels, one channel tile); (300, 512, 200): 3 row tiles x 2
+    # channel tiles x 16 k-blocks on tcgen05; K = 4 and K = 37 are not 16-byte rows: CUDA-core kernel
+    for (r, k, n) in [(1, 256, 10), (7, 256, 10), (300, 512, 200), (3, 4, 3), (130, 37, 65)]:
         a = rng.standard_normal((r, k), dtype=np.float32)
         b = rng.standard_normal((k, n), dtype=np.float32)
         bias = rng.standard_normal((1, n), dtype=np.float32)
@@ -179,6 +181,43 @@ def test_matmul(ctx):
         assert_close(L.matmul(ctx, ctx.tensor(a), ctx.tensor(b)).numpy(), want, f"matmul {r}x{k}x{n}")
         assert_close(L.matmul(ctx, ctx.tensor(a), ctx.tensor(b), bias=ctx.tensor(bias)).numpy(), want + bias,
                      f"matmul+bias {r}x{k}x{n}")
+
+
+def test_matmul_weight_cache_follows_uploads(ctx):
+    """The split / permuted tcgen05 weight tiles are cached on the right operand: a new upload must invalidate them."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((5, 64), dtype=np.float32)
+    tb = ctx.tensor(rng.standard_normal((64, 16), dtype=np.float32))
+    ta = ctx.tensor(a)
+    L.matmul(ctx, ta, tb)
+    b2 = rng.standard_normal((64, 16), dtype=np.float32)
+    tb.upload(b2)
+    assert_close(L.matmul(ctx, ta, tb).numpy(), (a.astype(np.float64) @ b2.astype(np.float64)), "matmul after re-upload")
+
+
+def test_upload_into_channel_view_leaves_siblings_alone(ctx):
+    """A channel view has the parent's pitch: uploading into it must write exactly its own lanes (the staged upload used
+    to zero-fill [0, ld) from the view's base: sibling channels zeroed, and an out-of-bounds write on the last pixel)."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(9)
+    for (C, off, ln) in [(12, 4, 4), (10, 3, 5), (8, 0, 6)]:
+        full = rng.standard_normal((2, C, 5, 7), dtype=np.float32)
+        parent = ctx.tensor(full)
+        part = rng.standard_normal((2, ln, 5, 7), dtype=np.float32)
+        parent.view_channels(off, ln).upload(part)
+        want = full.copy(); want[:, off:off + ln] = part
+        assert np.array_equal(parent.numpy(), want), (C, off, ln)
+        assert np.array_equal(parent.view_channels(off, ln).numpy(), part)
+
+
+def test_context_close_before_tensor_gc():
+    """Tensors keep their context alive: closing the context first and freeing the tensor later is not a use-after-free."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    c = L.Context(0)
+    t = c.tensor(np.ones((1, 4, 2, 2), np.float32))
+    c.close()
+    t.free()
 
 
 def test_reshape_concat_dropout(ctx):
