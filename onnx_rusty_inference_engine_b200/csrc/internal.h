@@ -99,6 +99,12 @@ int tc_supported(const ConvArgs& a);
 int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::shared_ptr<TcWeights>* out);
 int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st);
 
+// mnist8_fused.cu -- the MNIST-8 graph in two launches (config 5: small-kernel regime)
+size_t mnist8_p1_floats(int N);   // floats of the zero-haloed stem output [N][18][18][8] (+ 64 B per image), N rounded up to 8
+int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st);
+int launch_mnist8_head(const float* p1, const TcWeights& w2, const float* bias2, const float* add2, const float* wm, const float* bm,
+                       float* out, int N, cudaStream_t st);
+
 // ---------------------------------------------------------------- geometry with the reference's quirks
 struct Geo { int Ho, Wo, pt, pb, pl, pr; };
 // conv2d / max_pool2d output dims and effective zero padding (convolution_op.rs:293-324,:519-557;

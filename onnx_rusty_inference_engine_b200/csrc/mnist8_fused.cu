@@ -1,0 +1,441 @@
+// Fused path for the small-kernel regime (BASELINE.json config 5: MNIST-8, batch 65,536): the whole 12-node graph in
+// TWO launches that never write an un-pooled activation to HBM.
+//
+//   mnist8_stem_kernel   Conv(1->8, 5x5, SAME_UPPER) + Add[8,1,1] + Relu + MaxPool 2x2/2            CUDA cores (C = 1:
+//                        (Convolution28, Plus30, ReLU32, Pooling66)                                  K = 25, N = 8 is far
+//                        convolution_op.rs:224-517 (C == 1 branch :416-419), add_op.rs:75,           below one UMMA tile)
+//                        relu_op.rs:31-33, max_pool_op.rs:157-360
+//   mnist8_head_kernel   Conv(8->16, 5x5, SAME_UPPER) + Add[16,1,1] + Relu + MaxPool 3x3/3           tcgen05 3xTF32,
+//                        + Reshape + MatMul(256x10) + Add[1,10]                                      K = 200, N = 16
+//                        (Convolution110, Plus112, ReLU114, Pooling160, Times212_reshape0, Times212, Plus214)
+//                        + reshape_op.rs:66-92, mul_op.rs:23, add_op.rs:84
+//
+// Between the two: the pooled stem output in a zero-haloed channels-last layout [N][18][18][8] (+ 64 bytes per image, see
+// IMG_STRIDE), 10.4 KB per image, written once and read once.  The regime is instruction-issue-bound, not HBM-bound
+// (3.2 KB in, 40 B out per image), so the design minimises issued instructions:
+//   * stem: one thread = one pooled pixel = a 6x6 input patch in registers, 2x2 conv pixels x 8 channels = 32
+//     accumulators, weights as broadcast 128-bit shared loads; 8 images per block iteration = 7 full passes of 224 threads.
+//   * head: conv2 as an implicit GEMM whose 128-row tiles are (8 images x 16 pool windows) at ONE of the 9 positions
+//     inside a 3x3 pool window.  MaxPool 3x3/3 is then an element-wise max over the 9 tiles' accumulators in the epilogue
+//     threads' registers -- no cross-lane traffic, no pooled-out pixels computed (rows / columns 12, 13 of the 14x14 map
+//     never reach the output: max_pool_op.rs:215-246 floors) -- and the MatMul is 160 FMAs per thread plus a 4-lane
+//     shuffle reduction.  A operand: 16 producer warps in 4 sets read the group's 83 KB from shared memory (one bulk
+//     copy per 8 images), split hi / lo in registers and write tensor memory (tcgen05.st), exactly the K layout of
+//     conv_tc.cu, so the weight preparation (tc_prepare_weights) is shared.  MMAs: per k-step A_hi x [B_hi; B_lo]
+//     (N = 32) and A_lo x B_hi (N = 16): 25.5 + 17.7 clk measured (profiles/r2_mma_issue_rates.txt).
+// Numerics: 3xTF32 with {main | correction} accumulators like conv_tc.cu; bias / Add, Relu and the max commute
+// (x -> fl(x + b) and Relu are monotone), so max-then-add equals the reference's add-then-max bit for bit.
+#include <cstring>
+
+#include "internal.h"
+#include "tc_common.h"
+
+namespace b200 {
+namespace {
+
+#include "tc_ptx.cuh"
+
+// ------------------------------------------------------------------------------------------------ geometry (MNIST-8)
+constexpr int IN_HW = 28;                 // input 1 x 28 x 28
+constexpr int C1 = 8;                     // stem channels
+constexpr int P1_HW = 14;                 // pooled stem map
+constexpr int PADW = 18;                  // 14 + 2 * 2 halo
+constexpr int IMG_FLOATS = PADW * PADW * C1 + 16;   // 2,608 floats = 10,432 B: the 64 extra bytes make images 2k and 2k+1
+                                                     // differ by 64 B mod 128, so the two rows a quarter-warp reads in one
+                                                     // shared-memory phase (images 2k, 2k+1, same pixel) never share a bank
+constexpr int G = 8;                      // images per group = one 128-row tile per pool-window position
+constexpr int C2 = 16;                    // head conv channels
+constexpr int K2 = 200;                   // 5 * 5 * 8
+constexpr int NKB = 7;                    // k-blocks of 32 floats (4 taps) per tile
+constexpr int NOUT = 10;
+
+// ------------------------------------------------------------------------------------------------ stem (CUDA cores)
+constexpr int STEM_THREADS = 224;         // 8 images x 196 pooled pixels = 7 x 224
+constexpr int TILE_W = 32;                // 28 + 2 * 2 halo, padded rows of 32 floats
+
+struct StemArgs {
+  const float* x;        // [N][28*28]
+  const float* w;        // [8][25]   (conv weights [M][kh][kw][1])
+  const float* bias;     // [8] or null (Conv bias, convolution_op.rs:705)
+  const float* add;      // [8] or null (folded Add, add_op.rs:75)
+  float* p1;             // [N][IMG_FLOATS], halo and tail pre-zeroed, interior written here
+  int N;
+};
+
+__global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const StemArgs a) {
+  __shared__ __align__(16) float tile[G][TILE_W * TILE_W];   // zero-haloed input images
+  __shared__ __align__(16) float ws[25][8];                   // weights, tap-major: two broadcast LDS.128 per tap
+  __shared__ float sb[8], sa[8];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < G * TILE_W * TILE_W; i += STEM_THREADS) (&tile[0][0])[i] = 0.f;
+  for (int i = tid; i < 200; i += STEM_THREADS) ws[i >> 3][i & 7] = __ldg(a.w + (i & 7) * 25 + (i >> 3));
+  if (tid < 8) { sb[tid] = a.bias ? __ldg(a.bias + tid) : 0.f; sa[tid] = a.add ? __ldg(a.add + tid) : 0.f; }
+  const int groups = (a.N + G - 1) / G;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    __syncthreads();   // the previous group's compute has finished reading the tiles (and the first zero fill is visible)
+    // ---- stage 8 images: coalesced 128-bit reads (a 28-float row is 7 float4), interior of the zero-haloed tiles
+    const int img0 = g * G;
+    const int nimg = min(G, a.N - img0);
+    const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)img0 * (IN_HW * IN_HW));
+    for (int i = tid; i < nimg * 196; i += STEM_THREADS) {
+      const float4 v = __ldg(src + i);
+      const int im = i / 196, q = i - im * 196, r = q / 7, c4 = q - r * 7;
+      float* d = &tile[im][(r + 2) * TILE_W + 2 + c4 * 4];   // 8-byte aligned
+      *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
+      *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    // ---- 7 passes: task = (image, pooled pixel)
+#pragma unroll 1
+    for (int pass = 0; pass < 7; ++pass) {
+      const int task = pass * STEM_THREADS + tid;
+      const int im = task / 196, pp = task - im * 196, ph = pp / P1_HW, pw = pp - ph * P1_HW;
+      if (im >= nimg) continue;
+      // 6 x 6 patch: rows 2ph .. 2ph+5, columns 2pw .. 2pw+5 of the haloed tile
+      float in[6][6];
+      const float* t0 = &tile[im][(2 * ph) * TILE_W + 2 * pw];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(t0 + r * TILE_W + c);
+          in[r][c] = v.x; in[r][c + 1] = v.y;
+        }
+      float acc[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[p][c] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 5 + s][0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 5 + s][4]);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xv = in[(p >> 1) + r][(p & 1) + s];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+          }
+        }
+      // (conv + bias) + add, Relu, max over the 2 x 2 window (fold from -FLT_MAX like max_pool_op.rs:337)
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float m = -3.402823466e+38f;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) m = fmaxf(m, fmaxf((acc[p][c] + sb[c]) + sa[c], 0.f));
+        o[c] = m;
+      }
+      float* dst = a.p1 + (size_t)(img0 + im) * IMG_FLOATS + ((ph + 2) * PADW + (pw + 2)) * C1;
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head (tcgen05)
+constexpr int HEAD_WARPS = 24;
+constexpr int HEAD_THREADS = HEAD_WARPS * 32;   // 768
+constexpr int EPI_WARPS = 4;                    // warps 0-3: TMEM lane quarter = warp
+constexpr int LOAD_WARP = 4, MMA_WARP = 5;      // warps 6, 7 idle (producers must start at a multiple of 4)
+constexpr int PROD_WARP0 = 8;
+constexpr int NSETS = 4, SET_WARPS = 4;         // 16 producer warps: set j fills k-blocks j, j + 4, ...
+constexpr int SA = 4;                           // A stages in tensor memory (one per set), 64 columns each: hi 32 | lo 32
+constexpr int NACC = 4;                         // accumulator stages, 32 columns each: main 16 | correction 16
+constexpr int A_COL0 = NACC * 32;
+constexpr uint32_t IMG_BYTES = IMG_FLOATS * 4;  // 10,432
+constexpr uint32_t GROUP_BYTES = G * IMG_BYTES; // 83,456
+constexpr uint32_t B_KB_BYTES = 2 * C2 * 128;   // one k-block of weights: [B_hi 16 rows | B_lo 16 rows] x 128 B
+constexpr uint32_t SM_B = 0;                                    // 7 x 4 KB
+constexpr uint32_t SM_P1 = SM_B + NKB * B_KB_BYTES;             // 2 x 83,456 B
+constexpr uint32_t SM_WM = SM_P1 + 2 * GROUP_BYTES;             // matmul weights [10][256] + bias [10] (+ pad)
+constexpr uint32_t SM_ADD = SM_WM + (NOUT * 256 + 16) * 4;      // conv bias [16] | add [16]
+constexpr uint32_t SM_PART = SM_ADD + 32 * 4;                   // [2][4 warps][8 img][10] partial logits
+constexpr uint32_t SM_TAP = SM_PART + 2 * 4 * 8 * NOUT * 4;     // tap offsets [7][4] (bytes) | tile offsets [9] (bytes)
+constexpr uint32_t SM_BARS = SM_TAP + (28 + 12) * 4;
+constexpr int NBARS = 1 + 2 + 2 + SA + SA + NACC + NACC;        // b_full | p1_full[2] | p1_empty[2] | full_a | empty_a | tmem_full | tmem_empty
+constexpr uint32_t SM_SLOT = SM_BARS + NBARS * 8;
+constexpr uint32_t HEAD_SMEM = SM_SLOT + 16 + 1024;             // + alignment slack
+
+struct HeadArgs {
+  const float* p1;       // [N][IMG_FLOATS]
+  const float* bias2;    // [16] or null
+  const float* add2;     // [16] or null
+  const float* wm;       // [10][256], k = window * 16 + c (the activation's physical flatten order, see do_matmul)
+  const float* bm;       // [10] or null
+  float* out;            // [N][10]
+  int N;
+};
+
+__global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __grid_constant__ CUtensorMap tmapB, const HeadArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (sbase - smem_u32(smem_raw));   // generic pointer to the same place
+  const uint32_t bars = sbase + SM_BARS;
+  const uint32_t b_full = bars;
+  auto p1_full = [&](int b) { return bars + 8u * (1 + b); };
+  auto p1_empty = [&](int b) { return bars + 8u * (3 + b); };
+  auto full_a = [&](int s) { return bars + 8u * (5 + s); };
+  auto empty_a = [&](int s) { return bars + 8u * (5 + SA + s); };
+  auto tmem_full = [&](int s) { return bars + 8u * (5 + 2 * SA + s); };
+  auto tmem_empty = [&](int s) { return bars + 8u * (5 + 2 * SA + NACC + s); };
+  const uint32_t tmem_slot = sbase + SM_SLOT;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int groups = (a.N + G - 1) / G;
+  int my_groups = 0;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) ++my_groups;
+
+  // ---- per-CTA constants
+  float* const wm_s = reinterpret_cast<float*>(gbase + SM_WM);
+  float* const add_s = reinterpret_cast<float*>(gbase + SM_ADD);
+  uint32_t* const tap_s = reinterpret_cast<uint32_t*>(gbase + SM_TAP);
+  for (int i = threadIdx.x; i < NOUT * 256; i += HEAD_THREADS) wm_s[i] = __ldg(a.wm + i);
+  if (threadIdx.x < NOUT) wm_s[NOUT * 256 + threadIdx.x] = a.bm ? __ldg(a.bm + threadIdx.x) : 0.f;
+  if (threadIdx.x < 16) { add_s[threadIdx.x] = a.bias2 ? __ldg(a.bias2 + threadIdx.x) : 0.f; add_s[16 + threadIdx.x] = a.add2 ? __ldg(a.add2 + threadIdx.x) : 0.f; }
+  if (threadIdx.x < 28) { const int t = threadIdx.x; tap_s[t] = t < 25 ? (uint32_t)(((t / 5) * PADW + (t % 5)) * C1 * 4) : 0u; }   // tap (r, s) -> byte offset
+  if (threadIdx.x >= 32 && threadIdx.x < 41) { const int j = threadIdx.x - 32; tap_s[28 + j] = (uint32_t)(((j / 3) * PADW + (j % 3)) * C1 * 4); }   // window position j
+
+  if (warp == LOAD_WARP) {
+    if (lane == 0) {
+      mbar_init(b_full, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(p1_full(b), 1); mbar_init(p1_empty(b), NSETS * SET_WARPS); }
+      for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), SET_WARPS); mbar_init(empty_a(s), 1); }
+      for (int s = 0; s < NACC; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp >= PROD_WARP0) {
+    // ================================================================ A producers: 4 sets x 4 warps
+    // Warp w owns TMEM lanes 32 * (w % 4) ..; a thread owns rows quarter*32 + 8i + lane/4 (i < 4) and, of each 128-byte
+    // k-block row, the 16-byte chunks (lane % 4) and 4 + (lane % 4).  Row rho of a tile = image rho % 8, pool window
+    // rho / 8; chunk c of k-block kb = tap 4 kb + c / 2, channels 4 (c % 2) .. + 3.
+    const int pw_ = warp - PROD_WARP0;
+    const int quarter = pw_ & 3, set = pw_ >> 2;
+    const int rsub = lane >> 2, cq = lane & 3;
+    uint32_t rowoff[4];   // byte offset of (image, window origin, channel half) inside a group buffer
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = quarter * 32 + i * 8 + rsub, img = row & 7, win = row >> 3;
+      rowoff[i] = (uint32_t)img * IMG_BYTES + (uint32_t)(((3 * (win >> 2)) * PADW + 3 * (win & 3)) * C1 * 4) + (uint32_t)((cq & 1) * 16);
+    }
+    const uint32_t t_a = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(A_COL0 + set * 64);   // this set's A stage
+    const int total_kb = my_groups * 9 * NKB;
+    uint32_t ph = 0;                    // phase of this set's stage (full_a / empty_a [set])
+    int kb = set, j = 0, gl = 0;        // position of k-block idx: k-block kb of tile j of the CTA's gl-th group
+    bool group_entered = false;
+    for (int idx = set; idx < total_kb; idx += NSETS) {
+      if (!group_entered) { mbar_wait(p1_full(gl & 1), (uint32_t)(gl >> 1) & 1u); group_entered = true; }
+      const uint32_t buf = sbase + SM_P1 + (uint32_t)(gl & 1) * GROUP_BYTES;
+      uint32_t joff, t0, t1;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(joff) : "r"(sbase + SM_TAP + 4u * (uint32_t)(28 + j)));
+      // chunk cq -> tap 4 kb + cq / 2 ; chunk 4 + cq -> tap 4 kb + 2 + cq / 2
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t0) : "r"(sbase + SM_TAP + 4u * (uint32_t)(kb * 4 + (cq >> 1))));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t1) : "r"(sbase + SM_TAP + 4u * (uint32_t)(kb * 4 + 2 + (cq >> 1))));
+      const bool z0 = kb * 4 + (cq >> 1) >= 25, z1 = kb * 4 + 2 + (cq >> 1) >= 25;   // past K: exact zeros (finite whatever the weights)
+      float4 x0[4], x1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t ad = buf + rowoff[i] + joff;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0[i].x), "=f"(x0[i].y), "=f"(x0[i].z), "=f"(x0[i].w) : "r"(ad + t0));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x1[i].x), "=f"(x1[i].y), "=f"(x1[i].z), "=f"(x1[i].w) : "r"(ad + t1));
+        if (z0) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (z1) x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // advance to this set's next k-block; on leaving a group, hand its buffer back once the loads above have delivered
+      int nkb_ = kb + NSETS, nj = j, ngl = gl;
+      if (nkb_ >= NKB) { nkb_ -= NKB; ++nj; if (nj == 9) { nj = 0; ++ngl; } }
+      const bool last_of_group = ngl != gl || idx + NSETS >= total_kb;
+      if (last_of_group) {
+        const uint32_t dep = (__float_as_uint(x0[0].w) ^ __float_as_uint(x0[3].w) ^ __float_as_uint(x1[0].w) ^ __float_as_uint(x1[3].w)) & (uint32_t)(a.N >> 31);   // always 0, opaque
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p1_empty(gl & 1) + dep);
+        group_entered = false;
+      }
+      mbar_wait(empty_a(set), ph ^ 1u);   // the MMAs that read this stage have completed
+      tc_fence_after();
+      split_store(t_a, x0);               // 64-byte half 0 of the k-block row: TMEM columns [0,16) hi / [32,48) lo
+      split_store(t_a + 16u, x1);         // half 1: columns [16,32) / [48,64)
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_a(set));
+      ph ^= 1u;
+      kb = nkb_; j = nj; gl = ngl;
+    }
+  } else if (warp == LOAD_WARP) {
+    // ================================================================ loader: weights once, then one bulk copy per group
+    if (lane == 0) {
+      mbar_expect_tx(b_full, NKB * B_KB_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) {
+        tma_load_2d(sbase + SM_B + (uint32_t)kb * B_KB_BYTES, &tmapB, b_full, kb * 32, 0);               // B_hi rows [0,16)
+        tma_load_2d(sbase + SM_B + (uint32_t)kb * B_KB_BYTES + C2 * 128, &tmapB, b_full, kb * 32, C2);   // B_lo rows [16,32)
+      }
+      int gl = 0;
+      for (int g = blockIdx.x; g < groups; g += gridDim.x, ++gl) {
+        const int b = gl & 1;
+        mbar_wait(p1_empty(b), ((uint32_t)(gl >> 1) & 1u) ^ 1u);
+        const int nimg = min(G, a.N - g * G);
+        const uint32_t bytes = (uint32_t)nimg * IMG_BYTES;   // rows of images past N keep stale (finite or not) data: never stored
+        mbar_expect_tx(p1_full(b), bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + SM_P1 + (uint32_t)b * GROUP_BYTES),
+                     "l"(a.p1 + (size_t)g * G * IMG_FLOATS), "r"(bytes), "r"(p1_full(b))
+                     : "memory");
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================================================ MMA issuer (whole warp walks, one elected lane issues)
+    const uint32_t idesc32 = instr_desc_tf32(2 * C2), idesc16 = instr_desc_tf32(C2);
+    const bool leader = elect_one();
+    const uint32_t b_lo0 = (((sbase + SM_B) >> 4) & 0x3FFFu) | (1u << 16);
+    mbar_wait(b_full, 0);
+    const int tiles = my_groups * 9;
+    int sa = 0;
+    uint32_t pha = 0;
+    for (int t = 0; t < tiles; ++t) {
+      const int as = t & (NACC - 1);
+      mbar_wait(tmem_empty(as), (((uint32_t)t / NACC) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_main = tmem_base + (uint32_t)(as * 32), d_corr = d_main + (uint32_t)C2;
+#pragma unroll
+      for (int kb = 0; kb < NKB; ++kb) {
+        mbar_wait(full_a(sa), pha);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t ah = tmem_base + (uint32_t)(A_COL0 + sa * 64), al = ah + 32u;
+          const uint32_t bl = b_lo0 + (uint32_t)kb * (B_KB_BYTES >> 4);
+          constexpr int KSTEPS_TAIL = 2;   // K = 200 = 6 k-blocks + 8 floats; K is permuted inside groups of 16 -> one whole group
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kb < NKB - 1 || kk < KSTEPS_TAIL) {
+              umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bl + 2 * kk), idesc32, (kb | kk) != 0 ? 1u : 0u);   // hi*hi -> main, hi*lo -> corr
+              umma_tf32_ts(d_corr, al + 8u * kk, sw128_desc(bl + 2 * kk), idesc16, 1u);                          // lo*hi -> corr
+            }
+          }
+        }
+        __syncwarp();
+        if (leader) umma_commit(empty_a(sa));
+        if (++sa == SA) { sa = 0; pha ^= 1u; }
+      }
+      if (leader) umma_commit(tmem_full(as));
+      __syncwarp();
+    }
+  } else if (warp < EPI_WARPS) {
+    // ================================================================ epilogue: max over the 9 tiles, Add, Relu, MatMul
+    // Lane = row rho = 32 warp + lane of every tile: image rho % 8 = lane % 8, pool window rho / 8 = 4 warp + lane / 8.
+    const int img = lane & 7, win = warp * 4 + (lane >> 3);
+    float* const part = reinterpret_cast<float*>(gbase + SM_PART);
+    int t = 0, gl = 0;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x, ++gl) {
+      float m[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) m[c] = -3.402823466e+38f;   // fold start of max_pool_op.rs:337
+      for (int j = 0; j < 9; ++j, ++t) {
+        const int as = t & (NACC - 1);
+        mbar_wait(tmem_full(as), ((uint32_t)t / NACC) & 1u);
+        tc_fence_after();
+        uint32_t acc[16], cor[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * 32);
+        tmem_ld16(ta, acc);
+        tmem_ld16(ta + 16u, cor);
+        tmem_ld_wait(acc, cor);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty(as));
+#pragma unroll
+        for (int c = 0; c < 16; ++c) m[c] = fmaxf(m[c], __uint_as_float(acc[c]) + __uint_as_float(cor[c]));
+      }
+      // (conv + bias) + add, Relu (monotone: applied after the max), then this thread's share of the 256-long dot products
+      float f[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) f[c] = fmaxf((m[c] + add_s[c]) + add_s[16 + c], 0.f);
+      float o[NOUT];
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        const float4* wr = reinterpret_cast<const float4*>(wm_s + n * 256 + win * 16);
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wr[q];
+          s = fmaf(f[4 * q], w4.x, s); s = fmaf(f[4 * q + 1], w4.y, s); s = fmaf(f[4 * q + 2], w4.z, s); s = fmaf(f[4 * q + 3], w4.w, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        o[n] = s;
+      }
+      float* pb = part + (gl & 1) * (4 * 8 * NOUT);
+      if (lane < 8) {
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) pb[(warp * 8 + lane) * NOUT + n] = o[n];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      const int tid = warp * 32 + lane;
+      if (tid < 8 * NOUT) {
+        const int im = tid / NOUT, n = tid - im * NOUT;
+        const float s = (pb[(0 * 8 + im) * NOUT + n] + pb[(1 * 8 + im) * NOUT + n]) + (pb[(2 * 8 + im) * NOUT + n] + pb[(3 * 8 + im) * NOUT + n]);
+        if (g * G + im < a.N) a.out[(size_t)(g * G + im) * NOUT + n] = s + wm_s[NOUT * 256 + n];   // Plus214, add_op.rs:84
+      }
+      (void)img;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == LOAD_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+size_t mnist8_p1_floats(int N) { return (size_t)((N + G - 1) / G) * G * IMG_FLOATS; }
+
+int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st) {
+  if (N <= 0) return 0;
+  StemArgs a{x, w, bias, add, p1, N};
+  const int groups = (N + G - 1) / G;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = groups < sms * 3 ? groups : sms * 3;
+  mnist8_stem_kernel<<<grid, STEM_THREADS, 0, st>>>(a);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_mnist8_head(const float* p1, const TcWeights& w2, const float* bias2, const float* add2, const float* wm, const float* bm,
+                       float* out, int N, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (w2.M != C2 || w2.K != K2 || w2.BN != C2 || w2.Mpad != C2 || w2.Kpad != NKB * 32)
+    B200_FAIL(B200_EINVAL, "mnist8 head: weights prepared for M=%d K=%d BN=%d", w2.M, w2.K, w2.BN);
+  static bool attr_set[64] = {false};
+  static int sm_count[64] = {0};
+  int dev = 0;
+  B200_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CUDA(cudaFuncSetAttribute(mnist8_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM));
+    B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    attr_set[dev] = true;
+  }
+  const int sms = (dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+  const int groups = (N + G - 1) / G;
+  HeadArgs a{p1, bias2, add2, wm, bm, out, N};
+  mnist8_head_kernel<<<groups < sms ? groups : sms, HEAD_THREADS, HEAD_SMEM, st>>>(w2.tmap, a);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

@@ -23,6 +23,7 @@
 
 #include "internal.h"
 #include "onnx_wire.h"
+#include "tc_common.h"
 
 namespace b200 {
 namespace {
@@ -64,6 +65,9 @@ struct Plan {
   bool in_direct = false;   // input needs no transform (C == 1 or H*W == 1): memcpy
   bool in_s2d = false;      // input transform writes the 2x2 space-to-depth layout (stride-2 stem convolution)
   int in_c0 = 0, in_h0 = 0, in_w0 = 0;   // logical C, H, W of the graph input (in_s2d)
+  // Fused small-CNN path (mnist8_fused.cu): the first launch reads the caller's NCHW input directly, so it replaces the
+  // input transform (its pointer is per call: outside the CUDA graph, like the transform)
+  std::function<int(const float*, cudaStream_t)> in_stem;
   float* out_ptr = nullptr; // dense [batch, out_per_image]
   int64_t out_per_image = 0;
   bool out_needs_nchw = false;
@@ -96,6 +100,7 @@ struct b200_model {
   int opt_fire_fusion = 1;
   int opt_alt_order = 1;
   int opt_s2d = 1;           // stride-2 stem convolution on a space-to-depth copy of the graph input     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
+  int opt_fused_cnn = 1;     // the MNIST-8 graph as two fused launches (mnist8_fused.cu) when the graph matches
   int opt_verbose = 0;
   float* stage_in = nullptr;  size_t stage_in_bytes = 0;   // device staging for host-to-host runs
   float* stage_out = nullptr; size_t stage_out_bytes = 0;
@@ -286,6 +291,8 @@ struct Planner {
   int do_gap(size_t i);
   int do_softmax(size_t i);
   int plan_concat_redirects();
+  int matmul_weights(const Val& b, int perm_C, int perm_HW, int K, int N, const std::string& key, float** out);
+  int try_plan_mnist8(bool* done);
 };
 
 int Planner::plan_concat_redirects() {
@@ -723,16 +730,7 @@ int Planner::do_matmul(size_t i) {
   // weight as [N][K] rows (K-contiguous), with the activation's (h,w,c) flatten order folded in if needed
   std::string key = "matw:" + n.input[1] + ":" + std::to_string(a->perm_C) + "x" + std::to_string(a->perm_HW);
   float* dw = nullptr;
-  if (!m->consts.count(key)) {
-    std::vector<float> h((size_t)N * K);
-    const std::vector<float>& src = *b->host2d;  // [K][N], k in the reference's (c,h,w) order
-    for (int k = 0; k < K; ++k) {
-      int kp = k;  // position of reference row k in the activation's physical row
-      if (a->perm_C > 0) { const int c = k / a->perm_HW, hw = k % a->perm_HW; kp = hw * a->perm_C + c; }
-      for (int nn = 0; nn < N; ++nn) h[(size_t)nn * K + kp] = src[(size_t)k * N + nn];
-    }
-    B200_TRY(upload_const(m, key, h, &dw));
-  } else dw = m->consts[key]->p;
+  B200_TRY(matmul_weights(*b, a->perm_C, a->perm_HW, K, N, key, &dw));
   // fuse the following Add of a [1,N] initializer (MNIST Plus214, add_op.rs:84)
   std::string out_name = n.output[0];
   std::string label = n.name.empty() ? n.output[0] : n.name;
@@ -777,6 +775,147 @@ int Planner::do_matmul(size_t i) {
              [c](cudaStream_t st) { return launch_conv_simt(c, st); });
   }
   env[out_name] = y;
+  return 0;
+}
+
+int Planner::matmul_weights(const Val& b, int perm_C, int perm_HW, int K, int N, const std::string& key, float** out) {
+  if (m->consts.count(key)) { *out = m->consts[key]->p; return 0; }
+  std::vector<float> h((size_t)N * K);
+  const std::vector<float>& src = *b.host2d;  // [K][N], k in the reference's (c,h,w) order
+  if ((int64_t)src.size() != (int64_t)K * N) B200_FAIL(B200_EINVAL, "MatMul weight %s: %zu floats, expected %lld", key.c_str(), src.size(), (long long)K * N);
+  for (int k = 0; k < K; ++k) {
+    int kp = k;  // position of reference row k in the activation's physical row
+    if (perm_C > 0) { const int c = k / perm_HW, hw = k % perm_HW; kp = hw * perm_C + c; }
+    for (int nn = 0; nn < N; ++nn) h[(size_t)nn * K + kp] = src[(size_t)k * N + nn];
+  }
+  return upload_const(m, key, h, out);
+}
+
+// ---------------------------------------------------------------- the MNIST-8 graph as two fused launches
+// Matches exactly: input [*,1,28,28] -> Conv(8x1x5x5, stride 1, pads 2) [-> Add [8,1,1]] -> Relu -> MaxPool 2x2/2
+//   -> Conv(16x8x5x5, stride 1, pads 2) [-> Add [16,1,1]] -> Relu -> MaxPool 3x3/3 -> Reshape [*,256]
+//   -> MatMul(Reshape(initializer) [256,10]) [-> Add [1,10]] = graph output, every link single-consumer.
+// Everything else keeps the node-by-node plan.  (BASELINE.json config 5; kernels and layout in mnist8_fused.cu.)
+int Planner::try_plan_mnist8(bool* done) {
+  *done = false;
+  if (!m->opt_fused_cnn || m->opt_conv_path == 1) return 0;
+  if (m->in_dims[1] != 1 || m->in_dims[2] != 28 || m->in_dims[3] != 28 || (m->in_dims[0] != 1 && m->in_dims[0] > 0)) return 0;
+  auto next = [&](const std::string& v, const char* op, size_t* idx) -> const WireNode* {
+    const WireNode* c = sole_consumer(v, idx);
+    return (c && c->op_type == op && !c->input.empty() && c->input[0] == v && !c->output.empty()) ? c : nullptr;
+  };
+  struct ConvStage { const WireNode* conv = nullptr; const WireTensor *w = nullptr, *bias = nullptr, *add = nullptr; std::string out; };
+  std::vector<size_t> used;
+  auto conv_stage = [&](const std::string& in, int C, int M, int HW, int pool_k, int pool_out, ConvStage* cs) -> bool {
+    size_t i;
+    const WireNode* c = next(in, "Conv", &i);
+    if (!c || c->input.size() < 2) return false;
+    cs->conv = c; used.push_back(i);
+    cs->w = m->wm.find_initializer(c->input[1]);
+    if (!cs->w) return false;
+    auto wd = init_dims(m->wm, *cs->w);
+    if (wd.size() != 4 || wd[0] != M || wd[1] != C || wd[2] != 5 || wd[3] != 5 || (int64_t)cs->w->f32.size() != (int64_t)M * C * 25) return false;
+    if (c->input.size() > 2) {
+      cs->bias = m->wm.find_initializer(c->input[2]);
+      if (!cs->bias || cs->bias->f32.size() != (size_t)M) return false;
+    }
+    b200_conv_params p;
+    if (parse_conv_attrs(*c, &p) || p.strides[0] != 1 || p.strides[1] != 1 || p.group > 1 || p.dilations[0] > 1 || p.dilations[1] > 1) return false;
+    Geo g;
+    int ap = p.auto_pad;
+    if (p.pads[0] > 0 || p.pads[1] > 0 || p.pads[2] > 0 || p.pads[3] > 0) ap = B200_PAD_NOTSET;
+    if (ref_geometry(ap, HW, HW, 5, 5, 1, 1, p.pads, &g) || g.Ho != HW || g.Wo != HW || g.pt != 2 || g.pl != 2 || g.pb != 2 || g.pr != 2) return false;
+    std::string v = c->output[0];
+    if (const WireNode* a = next(v, "Add", &i)) {
+      if (a->input.size() != 2) return false;
+      cs->add = m->wm.find_initializer(a->input[1]);
+      if (!cs->add) return false;
+      auto ad = init_dims(m->wm, *cs->add);
+      if (ad.size() != 3 || ad[0] != M || ad[1] != 1 || ad[2] != 1 || cs->add->f32.size() != (size_t)M) return false;
+      used.push_back(i); v = a->output[0];
+    }
+    const WireNode* r = next(v, "Relu", &i);
+    if (!r) return false;
+    used.push_back(i); v = r->output[0];
+    const WireNode* mp = next(v, "MaxPool", &i);
+    if (!mp) return false;
+    b200_pool_params pp;
+    if (parse_pool_attrs(*mp, &pp) || pp.kernel[0] != pool_k || pp.kernel[1] != pool_k || pp.strides[0] != pool_k || pp.strides[1] != pool_k) return false;
+    Geo pg;
+    if (ref_geometry(pp.auto_pad, HW, HW, pool_k, pool_k, pool_k, pool_k, pp.pads, &pg) || pg.Ho != pool_out || pg.Wo != pool_out || pg.pt || pg.pl || pg.pb || pg.pr) return false;
+    used.push_back(i);
+    cs->out = mp->output[0];
+    return true;
+  };
+  ConvStage s1, s2;
+  if (!conv_stage(m->input_name, 1, 8, 28, 2, 14, &s1)) return 0;
+  if (!conv_stage(s1.out, 8, 16, 14, 3, 4, &s2)) return 0;
+  size_t i;
+  const WireNode* rs = next(s2.out, "Reshape", &i);
+  if (!rs || rs->input.size() != 2) return 0;
+  const WireTensor* shp = m->wm.find_initializer(rs->input[1]);
+  if (!shp || shp->i64.size() < 2 || shp->i64[1] != 256 || (shp->i64[0] != 1 && shp->i64[0] != 0)) return 0;
+  used.push_back(i);
+  const WireNode* mm = next(rs->output[0], "MatMul", &i);
+  if (!mm || mm->input.size() != 2) return 0;
+  used.push_back(i);
+  // the right operand: Reshape(initializer), constant-folded by do_reshape (file order puts it first in mnist-8)
+  size_t ib = (size_t)-1;
+  for (size_t k = 0; k < m->wm.nodes.size(); ++k)
+    if (!m->wm.nodes[k].output.empty() && m->wm.nodes[k].output[0] == mm->input[1]) ib = k;
+  if (ib == (size_t)-1 || m->wm.nodes[ib].op_type != "Reshape" || m->wm.nodes[ib].input.size() != 2 || !m->wm.find_initializer(m->wm.nodes[ib].input[0])) return 0;
+  if (n_consumers[mm->input[1]] != 1) return 0;
+  B200_TRY(do_reshape(ib));
+  used.push_back(ib);
+  Val* bval = get(mm->input[1]);
+  if (!bval || !bval->host2d || bval->dims[0] != 256 || bval->dims[1] != 10) return 0;
+  std::string out_name = mm->output[0];
+  const WireTensor* bm = nullptr;
+  if (const WireNode* a = next(out_name, "Add", &i)) {
+    if (a->input.size() != 2) return 0;
+    bm = m->wm.find_initializer(a->input[1]);
+    if (!bm) return 0;
+    auto bd = init_dims(m->wm, *bm);
+    if (bd.size() != 2 || bd[0] != 1 || bd[1] != 10 || bm->f32.size() != 10) return 0;
+    used.push_back(i); out_name = a->output[0];
+  }
+  if (m->wm.outputs.empty() || m->wm.outputs[0].name != out_name) return 0;
+  if (used.size() != m->wm.nodes.size()) return 0;   // nothing else in the graph
+  // ---- committed: constants (shared with the node-by-node plan through the keyed caches)
+  float *dw1 = nullptr, *db1 = nullptr, *da1 = nullptr, *dw2 = nullptr, *db2 = nullptr, *da2 = nullptr, *dwm = nullptr, *dbm = nullptr;
+  B200_TRY(conv_weights(*s1.w, {8, 1, 5, 5}, 1, &dw1));
+  if (s1.bias) B200_TRY(vec_const(*s1.bias, 8, &db1));
+  if (s1.add) B200_TRY(vec_const(*s1.add, 8, &da1));
+  B200_TRY(conv_weights(*s2.w, {16, 8, 5, 5}, 8, &dw2));
+  if (s2.bias) B200_TRY(vec_const(*s2.bias, 16, &db2));
+  if (s2.add) B200_TRY(vec_const(*s2.add, 16, &da2));
+  B200_TRY(matmul_weights(*bval, 16, 16, 256, 10, "matw:" + mm->input[1] + ":16x16", &dwm));
+  if (bm) B200_TRY(vec_const(*bm, 10, &dbm));
+  const int N = (int)B;
+  float* p1 = arena_alloc(mnist8_p1_floats(N));
+  Val y; y.rank = 2; y.dims[0] = B; y.dims[1] = 10;
+  B200_TRY(place(out_name, &y));
+  for (size_t k : used) consumed.insert(k);
+  env[out_name] = y;
+  if (dry) { ++step_counter; return *done = true, 0; }
+  std::shared_ptr<TcWeights> tcw;
+  {
+    const std::string key = "tc:" + s2.w->name + ":8";
+    auto it = m->tc_weights.find(key);
+    if (it == m->tc_weights.end()) {
+      B200_TRY(tc_prepare_weights(dw2, 16, 200, m->ctx->stream, &tcw));
+      m->tc_weights[key] = tcw;
+    } else tcw = it->second;
+  }
+  // the halo (and the 64 pad bytes per image) of the stem output are zero for the plan's lifetime: nothing else writes them
+  B200_CUDA(cudaMemsetAsync(p1, 0, mnist8_p1_floats(N) * sizeof(float), m->ctx->stream));
+  plan->in_stem = [=](const float* d_in, cudaStream_t st) { return launch_mnist8_stem(d_in, dw1, db1, da1, p1, N, st); };
+  float* dout = y.v.p;
+  const double flops = 2.0 * N * (8.0 * 25 * 784 + 16.0 * 200 * 196 + 256.0 * 10);   // the reference's 1.573 MFLOP per image
+  const double bytes = 4.0 * N * (784.0 + 10.0) + 4.0 * (200 + 3200 + 2560);
+  add_step("mnist8_head(Convolution110+Plus112+ReLU114+Pooling160+Times212+Plus214)", "mnist8_fused", flops, bytes,
+           [=](cudaStream_t st) { return launch_mnist8_head(p1, *tcw, db2, da2, dwm, dbm, dout, N, st); });
+  *done = true;
   return 0;
 }
 
@@ -955,6 +1094,9 @@ int Planner::run() {
     for (auto& d : drop) redirect.erase(d);
   }
 
+  plan->in_stem = nullptr;
+  bool fused_cnn = false;
+  B200_TRY(try_plan_mnist8(&fused_cnn));
   for (size_t i = 0; i < m->wm.nodes.size(); ++i) {
     if (consumed.count(i)) continue;
     const WireNode& n = m->wm.nodes[i];
@@ -1039,7 +1181,10 @@ int run_steps(b200_model* m, Plan* plan, cudaStream_t st) {
 int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out, cudaEvent_t input_consumed = nullptr) {
   cudaStream_t st = m->ctx->stream;
   // 1. input: logical NCHW (what the reference's manage_input_data holds, utils.rs:29-45) -> channels-last rows
-  if (plan->in_direct) {
+  if (plan->in_stem) {
+    B200_TRY(plan->in_stem(d_in, st));
+    m->ctx->launches++;
+  } else if (plan->in_direct) {
     B200_CUDA(cudaMemcpyAsync(plan->in_view.p, d_in, (size_t)plan->in_view.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else if (plan->in_s2d) {
     B200_TRY(launch_nchw_to_s2d(d_in, plan->in_view.N, plan->in_c0, plan->in_h0, plan->in_w0, plan->in_view.p, st));
@@ -1154,6 +1299,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
   } else if (k == "alt_order") {
     if (m->opt_alt_order != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_alt_order = value ? 1 : 0;
+  } else if (k == "fused_cnn") {
+    if (m->opt_fused_cnn != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_fused_cnn = value ? 1 : 0;
   } else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
   else B200_FAIL(B200_EINVAL, "unknown option %s", key);
   return 0;
@@ -1296,7 +1444,7 @@ int64_t b200_model_launches_per_run(b200_model* m, int64_t batch) {
   Guard g(m->ctx);
   Plan* p = nullptr;
   if (build_plan(m, batch, &p)) return B200_EINVAL;
-  return (int64_t)p->steps.size() + (p->in_direct ? 0 : 1);
+  return (int64_t)p->steps.size() + ((p->in_direct && !p->in_stem) ? 0 : 1);
 }
 
 int b200_model_profile(b200_model* m, int64_t batch, int iters, int flush_l2, char* buf, size_t cap) {

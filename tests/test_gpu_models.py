@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, MNIST_ONNX, assert_close
+from conftest import GOLDEN, MNIST_ONNX, assert_close, assert_close_mnist_noise
 
 pytestmark = pytest.mark.gpu
 
@@ -77,12 +77,35 @@ def test_mnist_batch_vs_oracle(ctx):
     want = rm.run_batch(ow.load_model(MNIST_ONNX), xs, ["Input3", "Parameter193"], threads=4)
     eng = Engine(MNIST_ONNX, ctx=ctx)
     got = eng(xs)
-    assert_close(got, want, "mnist batch 64")
-    assert (got.argmax(1) == want.argmax(1)).all()
+    assert_close_mnist_noise(got, want, "mnist batch 64")
     one = eng(xs[17:18])
     assert np.array_equal(one[0], got[17]), "batch-position invariance (bitwise)"
     big = eng(np.tile(xs, (64, 1, 1, 1)))          # 4096 images: same 64 answers, 64 times
     assert np.array_equal(big.reshape(64, 64, 10), np.broadcast_to(got, (64, 64, 10)))
+
+
+@pytest.mark.parametrize("batch", [1, 7, 8, 9, 300])
+def test_mnist_fused_path_vs_oracle_and_node_plan(ctx, batch):
+    """Config 5's fused path (mnist8_fused.cu: the 12-node graph as two launches, conv2 + pool + MatMul on tcgen05) against
+    the oracle and against the node-by-node plan of the same model, on ragged batch sizes (groups of 8 images: a partial
+    last group, a single image); bitwise batch-position invariance."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(batch, chw=(1, 28, 28), seed=100 + batch)
+    want = rm.run_batch(ow.load_model(MNIST_ONNX), xs, ["Input3", "Parameter193"], threads=8)
+    eng = Engine(MNIST_ONNX, ctx=ctx)
+    assert eng.model.launches_per_run(batch) == 2, "the fused path should be two launches"
+    got = eng(xs)
+    assert_close_mnist_noise(got, want, f"mnist fused, batch {batch}")
+    unit = synth.synthetic_batch(batch, chw=(1, 28, 28), seed=200 + batch, std=1.0)   # unit-scale input: plain tolerance
+    assert_close(eng(unit), rm.run_batch(ow.load_model(MNIST_ONNX), unit, ["Input3", "Parameter193"], threads=8), f"mnist fused, unit-scale input, batch {batch}")
+    assert np.array_equal(eng(xs), got), "run-to-run determinism"
+    k = batch // 2
+    assert np.array_equal(eng(xs[k:k + 1])[0], got[k]), "batch-position invariance (bitwise)"
+    eng.model.set_option("fused_cnn", 0)
+    assert eng.model.launches_per_run(batch) == 5
+    assert_close_mnist_noise(eng(xs), want, f"mnist node-by-node plan, batch {batch}")
 
 
 def test_squeezenet_synth_vs_oracle(ctx, synth_onnx):

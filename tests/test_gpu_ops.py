@@ -175,6 +175,8 @@ def test_matmul(ctx):
     for (r, k, n) in [(1, 256, 10), (7, 256, 10), (300, 512, 200), (3, 4, 3), (130, 37, 65)]:
         a = rng.standard_normal((r, k), dtype=np.float32)
         b = rng.standard_normal((k, n), dtype=np.float32)
+        if k > 256:   # keep the partial sums O(1): with unit-variance operands and K = 512 the fp32 summation-order noise
+            b /= np.float32(np.sqrt(k))   # on near-zero results alone exceeds 1e-4 relative (any two fp32 kernels disagree)
         bias = rng.standard_normal((1, n), dtype=np.float32)
         want = np.empty((r, n), np.float32)
         R.lib().ref_matmul(R._p(a), R._p(b), r, k, n, R._p(want))

@@ -87,6 +87,208 @@ __global__ void __launch_bounds__(128, 1) umma_rate(int N, int M, int mode, int 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// What do the per-k-block handshakes of a real pipeline cost the issuing warp?  A ring of 4 stages like conv_tc's A
+// ring: a producer warp arrives on full[s] as soon as empty[s] (committed by the MMA warp) lets it, so it runs up to 4
+// stages ahead and the consumer's waits are on barriers that completed long ago.  Per iteration the issuing warp does
+// nwait try_wait loops (all lanes when whole_warp, as conv_tc does), tcgen05.fence, `group` TS-mode MMAs from one
+// elected lane, and ncommit tcgen05.commit.  Reports clk per iteration next to the tensor pipe's own time for the MMAs:
+// (iteration - pipe) is what the handshakes cost when they are NOT hidden behind the asynchronous MMAs.
+__global__ void __launch_bounds__(128, 1) umma_sync_cost(int N, int group, int nwait, int ncommit, int iters, int whole_warp, long long* out, int flags = 0) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  const uint32_t b_smem = base + 16384;
+  const uint32_t bars = base + 16384 + 32768;   // done | full[4] | full2[4] | empty[4] | empty2[4]
+  const uint32_t slot = bars + 8 * 20;
+  auto full = [&](int s) { return bars + 8u * (1 + s); };
+  auto full2 = [&](int s) { return bars + 8u * (5 + s); };
+  auto empty = [&](int s) { return bars + 8u * (9 + s); };
+  auto empty2 = [&](int s) { return bars + 8u * (13 + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4 * i), "r"(0));
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 17; ++i) mbar_init(bars + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (warp == 1) {
+    if (lane == 0 && nwait > 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(empty(s), ph ^ 1u);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full(s)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full2(s)) : "memory");
+        if (++s == 4) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_tf32(N, 128);
+    const uint32_t d = tmem, a_t = tmem + 480u;
+    const uint64_t bd = sw128_desc(b_smem);
+    __syncwarp();
+    const long long t0 = clock64();
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (whole_warp || leader) {
+        if (nwait >= 1) mbar_wait(full(s), ph);
+        if (nwait >= 2) mbar_wait(full2(s), ph);
+      }
+      if (!(flags & 1)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (leader) {
+        if (flags & 4) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) umma_ts(d, a_t + 8u * (u & 3), bd + (uint64_t)(2 * (u & 3)), idesc, 1u);
+        } else
+        for (int u = 0; u < group; ++u) umma_ts(d, a_t + 8u * (u & 3), bd + (uint64_t)(2 * (u & 3)), idesc, 1u);
+      }
+      if (whole_warp) __syncwarp();
+      if (leader && (!(flags & 2) || (it & 15) == 15)) {
+        umma_commit(empty(s));              // the producer's pacing barrier
+        if (ncommit >= 2) umma_commit(empty2(s));
+      }
+      if (++s == 4) { s = 0; ph ^= 1u; }
+    }
+    if (leader) umma_commit(bars);
+    __syncwarp();
+    mbar_wait(bars, 0);
+    const long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// Loop structures for a real MMA issuer: per k-block wait full[s] (a producer warp keeps 4-6 stages ahead), issue 4 k-steps
+// x {N1, N2} MMAs whose A address / B descriptor depend on the stage, commit empty[s].
+//   VARIANT 0: the whole warp walks the loop (waits by all lanes), one elected lane issues inside `if (leader)` (conv_tc r1)
+//   VARIANT 1: ONE thread runs the whole loop (branch taken once, outside the loop)
+//   VARIANT 2: as 1, and the wait for k-block i+1 is a test_wait issued BEFORE the MMAs of k-block i (consumed after them)
+template <int VARIANT>
+__global__ void __launch_bounds__(128, 1) umma_loop(int N1, int N2, int iters, long long* out, int S = 6, int delay = 0) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  const uint32_t b_smem = base + 16384;
+  const uint32_t bars = base + 16384 + 32768;
+  const uint32_t slot = bars + 8 * 20;
+  auto full = [&](int s) { return bars + 8u * (1 + s); };
+  auto empty = [&](int s) { return bars + 8u * (9 + s); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4 * i), "r"(0));
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 17; ++i) mbar_init(bars + 8u * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+  if (warp == 1) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(empty(s), ph ^ 1u);
+        if (delay) { const long long c0 = clock64(); while (clock64() - c0 < delay) {} }   // the producer's work on this stage
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full(s)) : "memory");
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 0) {
+    const uint32_t idesc1 = idesc_tf32(N1, 128), idesc2 = idesc_tf32(N2, 128);
+    const uint32_t d = tmem;
+    const uint32_t lo0 = ((b_smem >> 4) & 0x3FFFu) | (1u << 16);
+    auto desc = [](uint32_t lo) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(0x40004040u)); return r; };
+    const bool leader = elect_one();
+    __syncwarp();
+    const long long t0 = clock64();
+    if (VARIANT == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (leader) {
+          const uint32_t ah = tmem + 128u + (uint32_t)s * 64u, al = ah + 32u, bl = lo0 + (uint32_t)(s & 3) * 256u;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ts(d, ah + 8u * kk, desc(bl + 2 * kk), idesc1, 1u);
+            umma_ts(d + 64u, al + 8u * kk, desc(bl + 2 * kk), idesc2, 1u);
+          }
+        }
+        __syncwarp();
+        if (leader) umma_commit(empty(s));
+        if (++s == S) { s = 0; ph ^= 1u; }
+      }
+    } else if (leader) {
+      int s = 0; uint32_t ph = 0;
+      bool ready = false;
+      for (int it = 0; it < iters; ++it) {
+        if (!ready) mbar_wait(full(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ah = tmem + 128u + (uint32_t)s * 64u, al = ah + 32u, bl = lo0 + (uint32_t)(s & 3) * 256u;
+        int ns = s + 1; uint32_t nph = ph;
+        if (ns == S) { ns = 0; nph ^= 1u; }
+        if (VARIANT == 2) {
+          // test the next stage's barrier first; its predicate is consumed after the MMAs (one asm block keeps it a predicate)
+          uint32_t r;
+          asm volatile(
+              "{\n\t.reg .pred q, p;\n\t"
+              "mbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+              "setp.ne.b32 p, 1, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%5], %7, %11, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%4], [%6], %7, %12, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%5+8], %8, %11, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%4], [%6+8], %8, %12, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%5+16], %9, %11, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%4], [%6+16], %9, %12, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%3], [%5+24], %10, %11, p;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%4], [%6+24], %10, %12, p;\n\t"
+              "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%13];\n\t"
+              "selp.u32 %0, 1, 0, q;\n\t}\n"
+              : "=r"(r)
+              : "r"(full(ns)), "r"(nph), "r"(d), "r"(d + 64u), "r"(ah), "r"(al), "l"(desc(bl)), "l"(desc(bl + 2)), "l"(desc(bl + 4)),
+                "l"(desc(bl + 6)), "r"(idesc1), "r"(idesc2), "r"(empty(s))
+              : "memory");
+          ready = r != 0;
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ts(d, ah + 8u * kk, desc(bl + 2 * kk), idesc1, 1u);
+            umma_ts(d + 64u, al + 8u * kk, desc(bl + 2 * kk), idesc2, 1u);
+          }
+          umma_commit(empty(s));
+        }
+        s = ns; ph = nph;
+      }
+    }
+    __syncwarp();
+    if (leader) umma_commit(bars);
+    __syncwarp();
+    mbar_wait(bars, 0);
+    const long long t1 = clock64();
+    if (lane == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // legacy path: every warp issues mma.sync m16n8k8 tf32 with NACC independent accumulators
 template <int NACC>
 __global__ void __launch_bounds__(1024, 1) mma_sync_rate(int iters, long long* out, float* sink) {
@@ -111,13 +313,16 @@ __global__ void __launch_bounds__(1024, 1) mma_sync_rate(int iters, long long* o
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  const bool only_loops = argc > 1 && argv[1][0] == 'l';
   long long* d_out; float* sink;
   cudaMalloc(&d_out, 64); cudaMalloc(&sink, 64);
   long long h[4];
-  const int smem = 1024 + 16384 + 32768 + 256;
+  const int smem = 1024 + 16384 + 32768 + 512;
   cudaFuncSetAttribute(umma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int iters = 4096;
+  if (!only_loops) {
   printf("tcgen05.mma kind::tf32 M=128, %d instructions back to back per issuer, 148 CTAs\n", iters);
   printf("%-4s %-5s %-7s %12s %12s\n", "mode", "N", "issuers", "clk/mma(iss)", "clk/mma(done)");
   for (int mode = 0; mode < 2; ++mode)
@@ -132,6 +337,47 @@ int main() {
         cudaMemcpy(h, d_out, 32, cudaMemcpyDeviceToHost);
         printf("%-4s %-5d %-7d %12.1f %12.1f\n", mode ? "SS" : "TS", N, nissue, (double)h[0] / iters, (double)h[1] / iters);
       }
+  cudaFuncSetAttribute(umma_sync_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  printf("\nper-iteration cost in the issuing warp: `group` TS MMAs + handshakes (the producer waits for each commit, so one iteration = issue + pipe + commit + wake-up round trip when nothing overlaps)\n");
+  printf("%-5s %-6s %-6s %-8s %-10s %12s %12s\n", "N", "group", "nwait", "ncommit", "wholewarp", "clk/iter", "pipe-only");
+  for (int N : {16, 32, 96})
+    for (int group : {8, 12})
+      for (int whole : {0, 1})
+        for (int nw = 0; nw <= 2; ++nw)
+          for (int nc = 1; nc <= 2; ++nc) {
+            for (int rep = 0; rep < 2; ++rep) {
+              umma_sync_cost<<<148, 128, smem>>>(N, group, nw, nc, 2048, whole, d_out);
+              cudaError_t e = cudaDeviceSynchronize();
+              if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+            }
+            cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+            printf("%-5d %-6d %-6d %-8d %-10d %12.1f %12.1f\n", N, group, nw, nc, whole, (double)h[0] / 2048, group * (9.5 + N / 2.0));
+          }
+  }
+  cudaFuncSetAttribute(umma_loop<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(umma_loop<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(umma_loop<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  printf("\nissuer loop (whole warp walks, one elected lane issues): per k-block wait + 4 k-steps x {N1, N2} + commit; one producer thread, S stages, `delay` clk of work per stage; clk per k-block\n");
+  for (int pair = 0; pair < 3; ++pair) {
+    const int N1 = pair == 0 ? 32 : pair == 1 ? 128 : 256, N2 = N1 / 2;
+    for (int S : {2, 4, 6})
+      for (int delay : {0, 300, 600, 1200}) {
+        for (int rep = 0; rep < 2; ++rep) {
+          umma_loop<0><<<148, 128, smem>>>(N1, N2, 2048, d_out, S, delay);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+        }
+        cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+        printf("N1=%d N2=%d S=%d delay=%d: %.1f clk per k-block (pipe %.1f)\n", N1, N2, S, delay, (double)h[0] / 2048, 4 * (19.0 + N1 / 2.0 + N2 / 2.0));
+      }
+  }
+  if (only_loops) return 0;
+  printf("\nwhat costs the fixed part?  N=16, group 8, no waits: flags 1 = no tcgen05.fence, 2 = commit only every 16th iteration, 4 = MMAs unrolled\n");
+  for (int flags = 0; flags < 8; ++flags) {
+    for (int rep = 0; rep < 2; ++rep) { umma_sync_cost<<<148, 128, smem>>>(16, 8, 0, 1, 2048, 0, d_out, flags); cudaDeviceSynchronize(); }
+    cudaMemcpy(h, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("flags %d: %.1f clk/iter\n", flags, (double)h[0] / 2048);
+  }
   printf("\nmma.sync.m16n8k8 tf32, 148 CTAs\n%-6s %-5s %14s %16s\n", "warps", "nacc", "mma/clk/SM", "TFLOP/s@1.9GHz");
   for (int warps : {4, 8, 16, 32}) {
     const int it2 = 2048;
