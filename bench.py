@@ -96,6 +96,111 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+KERNEL_SOURCES = ("conv_tc.cu", "tc_ptx.cuh", "model.cu", "bandwidth_ops.cu", "layout.cu")
+
+
+def kernel_sources_sha() -> str:
+    """sha256 over the sources that decide the launch list and the conv tiling: a committed ncu traffic figure is only
+    quoted while it matches (it goes stale the moment the tiling changes)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "onnx_rusty_inference_engine_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def clock_regime(clocks) -> str:
+    """'burst' when the in-region clock samples show the SM clock at its maximum with no throttle reason, else
+    'sustained' (sw_power_cap / clock below max): picks which MEASURED_PEAKS.json tensor figure the fraction is against."""
+    if not clocks or not clocks.get("sm_mhz") or not clocks.get("sm_max_mhz"):
+        return "sustained"
+    if clocks.get("reasons"):
+        return "sustained"
+    return "burst" if clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] else "sustained"
+
+
+def mnist_extra(torch, dist, local, world, rank, peaks, stream, steps=20, warmup=3):
+    """BASELINE.json configs[4]: MNIST-8, 65,536 synthetic images split over the run's GPUs (8,192 per GPU at 8), inputs
+    resident, logits gathered on every rank inside the timed region.  Not the headline metric: an `extra` block."""
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    total = 65536
+    per = total // world
+    dev = torch.device("cuda", local)
+    eng = Engine(os.path.join(ROOT, "tests", "golden", "mnist-8.onnx"), device=local, stream=stream.cuda_stream)
+    in_bytes = per * 784 * 4
+    nbuf = max(2, -(-160 * (1 << 20) // in_bytes) + 1)      # the rotating inputs together exceed the 126 MB L2
+    g = torch.Generator(device=dev); g.manual_seed(3 + rank)
+    xs = [torch.randn((per, 1, 28, 28), generator=g, device=dev, dtype=torch.float32) * 10.0 for _ in range(nbuf)]
+    out = torch.empty((per, 10), device=dev, dtype=torch.float32)
+    gathered = torch.empty((total, 10), device=dev, dtype=torch.float32) if world > 1 else None
+
+    def step(i):
+        eng.run_torch(xs[i % nbuf], out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = eng.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / steps
+    assert torch.isfinite(out).all()
+    prof = eng.model.profile(per, iters=3, flush_l2=True)
+    value = total / (ms * 1e-3)
+    flops_img, bytes_img = 1.573e6, 3136.0 + 40.0        # SURVEY.md section 8(d): reference FLOPs, fused lower bound of traffic
+    tens_peak = peaks["bf16_tflops"] / 6.0
+    return {
+        "workload": f"MNIST-8 batch {total} synthetic 1x28x28 fp32 N(0,10^2), {per} per GPU (BASELINE.json configs[4])",
+        "value": value, "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup, "n_gpus": world,
+        "gpu_launches_per_step": (eng.ctx.launch_count() - l0) // steps,
+        "launches": [{"name": p["name"], "kind": p["kind"], "ms": p["ms"], "tflops": p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else None}
+                     for p in prof],
+        "roofline": {
+            "tensor": {"achieved_tflops": flops_img * total / (ms * 1e-3) / 1e12 / world, "peak_tflops": tens_peak,
+                       "frac": flops_img * total / (ms * 1e-3) / 1e12 / world / tens_peak,
+                       "per": "1.573 MFLOP per image (reference FLOPs: the 52 conv2 outputs per image that MaxPool 3x3/3 floors away are not computed), per GPU; peak = bf16 burst / 6 (3xTF32)"},
+            "hbm": {"achieved_gbs": bytes_img * total / (ms * 1e-3) / 1e9 / world, "peak_gbs": peaks["hbm_gbs"],
+                    "frac": bytes_img * total / (ms * 1e-3) / 1e9 / world / peaks["hbm_gbs"],
+                    "per": "3,176 B per image (input + logits: the fused lower bound), per GPU"},
+            "bound": "instruction issue / MMA issue (neither roofline binds: see DESIGN.md section 4.3)"},
+        "l2": f"{nbuf} rotating input batches of {in_bytes / 1e6:.1f} MB per GPU (> 126 MB L2 in total)",
+        "prev_round": {"value": 17.5e6, "note": "round 1, one GPU, 5 launches (DESIGN.md r1)"},
+    }
+
+
+def e2e_block(value, B, out_per_image, world, steps, path):
+    """The e2e figure with its own roofline: the host-to-device copy of the fp32 input batch is the bound (154 MB per 256
+    images per rank; the reference API takes Vec<f32>, so the bytes cannot shrink).  Ceiling = the per-rank pinned H2D
+    rate measured with that many ranks copying at once on this pool's 8 x B200 boxes (profiles/r2_h2d_concurrent.txt)."""
+    h2d = B * 3 * 224 * 224 * 4
+    d2h = B * out_per_image * 4 * (world if world > 1 else 1)       # rank 0 lands every rank's logits at N > 1
+    blk = {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps, "path": path}
+    cp = os.path.join(ROOT, "profiles", "r2_h2d_ceiling.json")
+    if os.path.exists(cp):
+        with open(cp) as f:
+            ceil = json.load(f)
+        per_rank = ceil.get("per_rank_gbs", {}).get(str(world))
+        if per_rank:
+            achieved = value / world * (h2d / B) / 1e9          # GB/s of input per rank
+            blk["roofline"] = {"bound": "pcie_h2d", "achieved": achieved, "peak": per_rank, "unit": "GB/s per rank",
+                               "frac": achieved / per_rank, "peak_source": ceil.get("how")}
+    return blk
+
+
 def workload_name(batch: int) -> str:
     return (f"SqueezeNet1.0-8 (seeded synthetic weights) batch {batch} per GPU, 3x224x224 fp32 "
             "N(0,10^2) (BASELINE.json configs[2])")
@@ -217,6 +322,21 @@ def run_own(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    shard_check = None
+    if world > 1:
+        # once, outside the timed region: rank 0 regenerates rank 1's batch (same Philox seed) and recomputes it alone;
+        # the rows NCCL gathered from rank 1 must be the same bits (sharded == single-GPU)
+        step(0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            g1 = torch.Generator(device=dev); g1.manual_seed(1234 + 1)
+            x1 = torch.randn((B, 3, 224, 224), generator=g1, device=dev, dtype=torch.float32) * 10.0
+            mine = eng.run_torch(x1)
+            torch.cuda.synchronize()
+            shard_check = bool(torch.equal(mine, gathered[B:2 * B])) and bool(torch.equal(out, gathered[0:B]))
+            assert shard_check, "rank 1's gathered logits differ from rank 0's recomputation of the same images"
+            del x1, mine
+        dist.barrier()
     launches0 = eng.ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -238,27 +358,68 @@ def run_own(args):
     value = world * B * K / (ms / 1e3)
     assert torch.isfinite(out).all()
 
-    # ---- e2e: the C-ABI host entry point, pinned host buffers, H2D and D2H inside the timed region
+    # ---- e2e: pinned host buffers, H2D and D2H inside the timed region
     xh = [torch.randn((B, 3, 224, 224), dtype=torch.float32).mul_(10.0).pin_memory() for _ in range(2)]
-    oh = torch.empty((B, eng.out_per_image), dtype=torch.float32).pin_memory()
-    ohs = [oh, torch.empty_like(oh).pin_memory()]
+    ohs = [torch.empty((B, eng.out_per_image), dtype=torch.float32).pin_memory() for _ in range(2)]
+    Ke = max(4, min(K, 100))
+    if world == 1:
+        # the C-ABI host entry point b200_model_run_async: every step copies ITS input batch from pinned host memory and ITS
+        # logits back; two steps are in flight, so the H2D of step i+1 overlaps the compute of step i
+        def e2e_step(i):
+            eng.run_pinned_async(xh[i % 2], ohs[i % 2])
+
+        def e2e_drain():
+            eng.sync()
+        e2e_path = "b200_model_run_async (C ABI): pinned host -> H2D -> run -> D2H, two steps in flight"
+    else:
+        # N > 1: the same pipeline driven from torch so that the logits gather north_star names is INSIDE the region:
+        # pinned host -> H2D (copy stream) -> Engine.run_torch -> NCCL all-gather -> D2H of all ranks' logits on rank 0
+        copy_s = torch.cuda.Stream(device=dev)
+        xd = [torch.empty((B, 3, 224, 224), device=dev, dtype=torch.float32) for _ in range(2)]
+        od = [torch.empty((B, eng.out_per_image), device=dev, dtype=torch.float32) for _ in range(2)]
+        gd = [torch.empty((world * B, eng.out_per_image), device=dev, dtype=torch.float32) for _ in range(2)]
+        gh = [torch.empty((world * B, eng.out_per_image), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        for ev in consumed:
+            ev.record(stream)
+
+        def e2e_step(i):
+            b = i % 2
+            copy_s.wait_event(consumed[b])                 # the run that read xd[b] two steps ago has finished
+            with torch.cuda.stream(copy_s):
+                xd[b].copy_(xh[b], non_blocking=True)
+                copied[b].record(copy_s)
+            stream.wait_event(copied[b])
+            eng.run_torch(xd[b], od[b])
+            consumed[b].record(stream)
+            dist.all_gather_into_tensor(gd[b], od[b])
+            if rank == 0:
+                gh[b].copy_(gd[b], non_blocking=True)
+
+        def e2e_drain():
+            torch.cuda.synchronize()
+        e2e_path = ("pinned host -> H2D on a copy stream -> Engine.run_torch -> NCCL all-gather of the logits -> D2H of all "
+                    "ranks' logits on rank 0; two steps in flight")
     for i in range(3):
-        eng.run_pinned_async(xh[i % 2], ohs[i % 2])
-    eng.sync()
+        e2e_step(i)
+    e2e_drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    Ke = max(4, min(K, 100))
     t0 = time.perf_counter()
     for i in range(Ke):
-        # b200_model_run_async: every step copies ITS input batch from pinned host memory and ITS logits back; two
-        # steps are in flight, so the H2D of step i+1 overlaps the compute of step i
-        eng.run_pinned_async(xh[i % 2], ohs[i % 2])
-    eng.sync()                          # all logits are in host memory
+        e2e_step(i)
+    e2e_drain()                          # all logits are in host memory
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(te.item())
+
+    extra = None
+    if not args.no_extra:
+        torch.cuda.synchronize()
+        extra = {"mnist_b65536": mnist_extra(torch, dist, local, world, rank, measured_peaks(), stream)}
 
     line = None
     if rank == 0:
@@ -273,7 +434,11 @@ def run_own(args):
         conv_flops = sum(p["flops"] for p in conv)
         total_ms = sum(p["ms"] for p in prof)
         top = max(prof, key=lambda p: p["ms"])
-        tensor_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0   # TF32 = bf16/2; 3xTF32 = three MMAs per useful MAC
+        # TF32 = bf16 / 2; 3xTF32 = three MMAs per useful MAC.  Which measured bf16 figure: the burst one when the in-region
+        # clock samples show max clock and no throttle reason, else the sustained one; both fractions are printed.
+        regime = clock_regime(clocks)
+        peak_burst, peak_sust = peaks["bf16_tflops"] / 6.0, peaks["bf16_tflops_sustained"] / 6.0
+        tensor_peak = peak_burst if regime == "burst" else peak_sust
         # The conv launches' duration INSIDE the timed region = the region's CUDA-event time per step x the conv
         # launches' share of the per-launch event profile (isolated launches pay launch latency and clock ramps that a
         # graph replay does not: their sum exceeds the step, their shares agree with the ncu launch list).
@@ -283,31 +448,48 @@ def run_own(args):
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
         bw = [p for p in prof if not p["kind"].startswith("conv") and not p["kind"].startswith("matmul")]
         bw_ms = sum(p["ms"] for p in bw)
-        if total_ms:
-            bw_ms = (ms / K) * (bw_ms / total_ms)   # same apportioning for the bandwidth kernels
+        scale = (ms / K) / total_ms if total_ms else 1.0
+        bw_ms *= scale                                   # same apportioning for the bandwidth kernels
         bw_gbs = sum(p["bytes"] for p in bw) / (bw_ms * 1e-3) / 1e9 if bw_ms > 0 else None
-        # DRAM bytes of the same launches from the committed ncu pass (profiles/README.md); null if absent
+        # per-launch table: in-order event time scaled to the step, each launch against the roofline that bounds it
+        table = []
+        for p in prof:
+            t = p["ms"] * scale
+            tf = p["flops"] / (t * 1e-3) / 1e12 if t > 0 else 0.0
+            gb = p["bytes"] / (t * 1e-3) / 1e9 if t > 0 else 0.0
+            bound = "tensor" if p["kind"].startswith(("conv", "matmul")) and p["flops"] / (tensor_peak * 1e12) > p["bytes"] / (peaks["hbm_gbs"] * 1e9) else "hbm"
+            table.append({"name": p["name"], "kind": p["kind"], "ms": round(t, 5), "tflops": round(tf, 2), "gbs": round(gb, 1), "bound": bound,
+                          "frac": round(tf / tensor_peak if bound == "tensor" else gb / peaks["hbm_gbs"], 3)})
+        floor_ms = sum(max(p["flops"] / (tensor_peak * 1e12), p["bytes"] / (peaks["hbm_gbs"] * 1e9)) for p in prof) * 1e3
+        # DRAM bytes of the same launches from the committed ncu pass -- only while the kernel sources are the ones it was
+        # taken on (profiles/r2_step_dram_traffic.json records their hash); null otherwise
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r1b_step_dram_traffic.json")
-        if os.path.exists(tp) and B == 256 and not args.conv_path:
+        tp = os.path.join(ROOT, "profiles", "r2_step_dram_traffic.json")
+        if os.path.exists(tp) and B == 256 and not args.conv_path and not args.model_opt:
             with open(tp) as f:
                 tj = json.load(f)
-            if tj.get("conv_tc_launches") == len(conv):
+            if tj.get("conv_tc_launches") == len(conv) and tj.get("kernel_sources_sha") == kernel_sources_sha():
                 traffic = tj.get("conv_tc_dram_bytes_per_step")
-                traffic_src = (f"profiles/r1b_step_dram_traffic.json (ncu dram__bytes_read+write.sum, the {len(conv)} conv "
-                               "launches of one step)")
+                traffic_src = (f"profiles/r2_step_dram_traffic.json (ncu dram__bytes_read+write.sum, the {len(conv)} conv "
+                               f"launches of one step; kernel sources {tj.get('kernel_sources_sha')})")
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": achieved / tensor_peak, "traffic": traffic, "traffic_source": traffic_src,
-            "algorithmic_bytes": sum(p["bytes"] for p in conv), "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel); duration = CUDA-event step time of the "
-                                                      "timed region x the launches' share of the in-order per-launch event profile",
+            "frac": achieved / tensor_peak, "regime": regime, "frac_burst": achieved / peak_burst, "frac_sustained": achieved / peak_sust,
+            "peak_burst": peak_burst, "peak_sustained": peak_sust,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes": sum(p["bytes"] for p in conv), "algorithmic_flops": conv_flops,
+            "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel); duration = CUDA-event step time of the "
+                   "timed region x the launches' share of the in-order per-launch event profile",
             "kernel": f"conv (all {len(conv)} Conv launches of one step, 26 Conv nodes: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
-            "peak_source": f"{peaks['src']}: bf16_tflops_sustained {peaks['bf16_tflops_sustained']} / 2 (TF32) / 3 (3xTF32)",
+            "peak_source": f"{peaks['src']}: bf16_tflops {peaks['bf16_tflops']} (burst) / bf16_tflops_sustained {peaks['bf16_tflops_sustained']}, / 2 (TF32) / 3 (3xTF32); "
+                           f"regime '{regime}' chosen from the in-region clock samples",
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_share, "conv_ms_isolated_launches": conv_ms_isolated,
-            "top_launch": {"name": top["name"], "kind": top["kind"], "ms": top["ms"],
-                           "tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else None},
+            "top_launch": {"name": top["name"], "kind": top["kind"], "ms": top["ms"] * scale,
+                           "tflops": top["flops"] / (top["ms"] * scale * 1e-3) / 1e12 if top["ms"] > 0 else None},
             "hbm_ops": {"achieved_gbs": bw_gbs, "peak_gbs": peaks["hbm_gbs"],
                         "frac": (bw_gbs / peaks["hbm_gbs"]) if bw_gbs else None, "ms_per_step": bw_ms},
+            "step_floor_ms": floor_ms, "step_frac_of_mixed_roofline": floor_ms / (ms / K),
+            "launches": table,
         }
         if args.profile_out:
             with open(args.profile_out, "w") as f:
@@ -329,10 +511,10 @@ def run_own(args):
                        "global_batch": world * B, "parallelism": f"batch-sharded x{world}, replicated weights",
                        "l2": "inputs (154 MB per batch, two alternating) and activations exceed the 126 MB L2",
                        "conv_path": args.conv_path},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4,
-                    "d2h_bytes_per_step": B * eng.out_per_image * 4, "steps": Ke},
+            "e2e": e2e_block(e2e_value, B, eng.out_per_image, world, Ke, e2e_path),
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_line,
+            "extra": extra, "shard_check_bitwise": shard_check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -352,6 +534,7 @@ def main():
     ap.add_argument("--profile-out", default=None, dest="profile_out")
     ap.add_argument("--model-opt", action="append", default=[], dest="model_opt")
     ap.add_argument("--no-cpu-baseline", action="store_true", dest="no_cpu_baseline")
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra")   # skip the MNIST config-5 block (ncu launch lists)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
