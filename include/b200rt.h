@@ -173,7 +173,14 @@ int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float
  * kernel, 2 = force tcgen05 3xTF32), "fire_fusion" (0/1, default 1: expand1x1 + expand3x3 of a Fire module as one
  * launch when both fit one channel tile), "s2d" (0/1, default 1: a stride-2 stem convolution runs on a 2x2
  * space-to-depth copy of the graph input), "alt_order" (0/1, default 1: launches walk their tiles in alternating
- * directions so that each starts on what its predecessor left in the L2), "verbose" (0/1: print the reference's per-node lines). */
+ * directions so that each starts on what its predecessor left in the L2), "fused_cnn" (0/1, default 1: the MNIST-8 graph as two
+ * fused launches when the graph matches), "finite_guard" (0/1, default 1: see below), "verbose" (0/1: print the reference's
+ * per-node lines).
+ * Finite guard: the tensor-core path splits every value into hi + lo (Inf - Inf = NaN) and some fusions add 0 * x terms, so
+ * it reproduces the reference for FINITE inputs; the reference itself keeps an Inf / NaN local to the outputs that really
+ * read it (convolution_op.rs:480).  Every run's input stage therefore checks the input: b200_model_run reruns a batch that
+ * holds an Inf / NaN on the CUDA-core fp32 plan (the reference's semantics, slower) by itself; b200_model_sync returns
+ * B200_EUNSUPPORTED when a batch run through the asynchronous entry points since the last sync held one. */
 int b200_model_set_option(b200_model *m, const char *key, int64_t value);
 /* Per-launch profile of the last planned batch size: runs each planned launch `iters` times between CUDA
  * events and writes one JSON document into buf.  flush_l2: 0 = repeat each launch back to back, 1 = flush the L2

@@ -79,7 +79,9 @@ struct PoolArgs {
 int launch_nchw_to_rows(const float* src_nchw, TView dst, bool zero_pad_lanes, cudaStream_t st);
 int launch_rows_to_nchw(TView src, float* dst_nchw, cudaStream_t st);
 // NCHW [N,C,H,W] (H, W even) -> 2x2 space-to-depth rows [N, H/2, W/2, 4*C], channel (dy*2+dx)*C + c
-int launch_nchw_to_s2d(const float* src_nchw, int N, int C, int H, int W, float* dst, cudaStream_t st);
+// nonfinite (optional): device int set to 1 when the input holds an Inf / NaN (see b200_model's finite guard)
+int launch_nchw_to_s2d(const float* src_nchw, int N, int C, int H, int W, float* dst, cudaStream_t st, int* nonfinite = nullptr);
+int launch_nonfinite_scan(const float* p, size_t n, int* flag, cudaStream_t st);
 int launch_copy_rows(TView src, TView dst, cudaStream_t st);          // same N,C,H,W; pitches may differ
 int launch_transpose2d(const float* src, int R, int C, float* dst, cudaStream_t st);  // dst[c][r] = src[r][c]
 // bandwidth_ops.cu
@@ -101,7 +103,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st);
 
 // mnist8_fused.cu -- the MNIST-8 graph in two launches (config 5: small-kernel regime)
 size_t mnist8_p1_floats(int N);   // floats of the zero-haloed stem output [N][18][18][8] (+ 64 B per image), N rounded up to 8
-int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st);
+int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st, int* nonfinite = nullptr);
 int launch_mnist8_head(const float* p1, const TcWeights& w2, const float* bias2, const float* add2, const float* wm, const float* bm,
                        float* out, int N, cudaStream_t st);
 

@@ -156,8 +156,10 @@ __global__ void nchw_to_s2d_kernel(const float* __restrict__ src, float* __restr
 // The same for C channels known at compile time (C = 3: the image stem): thread per output pixel, one 64-bit load per
 // (c, dy) -- a warp reads 256 contiguous bytes of an input row -- and 4*C/4 128-bit stores, 16*C contiguous bytes per pixel.
 template <int C>
-__global__ void nchw_to_s2d_fixed_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, long long pixels) {
+__global__ void nchw_to_s2d_fixed_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, long long pixels,
+                                         int* __restrict__ nonfinite) {
   const int W2 = W >> 1, H2 = H >> 1;
+  uint32_t mx = 0;   // largest |bits| seen: >= 0x7f800000 means Inf / NaN (the split-precision paths are exact for finite data only)
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(pix % W2);
     const long long t = pix / W2;
@@ -171,21 +173,44 @@ __global__ void nchw_to_s2d_fixed_kernel(const float* __restrict__ src, float* _
         const float2 pr = __ldg(reinterpret_cast<const float2*>(src + ((n * C + c) * H + 2 * y + dy) * (long long)W + 2 * x));
         v[(dy * 2 + 0) * C + c] = pr.x;
         v[(dy * 2 + 1) * C + c] = pr.y;
+        mx = max(mx, max(__float_as_uint(pr.x) & 0x7fffffffu, __float_as_uint(pr.y) & 0x7fffffffu));
       }
     float4* o = reinterpret_cast<float4*>(dst + pix * (4 * C));
 #pragma unroll
     for (int q = 0; q < C; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
+  if (nonfinite && mx >= 0x7f800000u) *nonfinite = 1;
 }
 
-int launch_nchw_to_s2d(const float* src, int N, int C, int H, int W, float* dst, cudaStream_t st) {
+// Any Inf / NaN in p[0, n)?  (input stages that have no kernel of their own to carry the check)
+__global__ void nonfinite_scan_kernel(const float* __restrict__ p, size_t n, int* __restrict__ nonfinite) {
+  uint32_t mx = 0;
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+    mx = max(max(mx, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu, max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) mx = max(mx, __float_as_uint(p[n4 * 4 + threadIdx.x]) & 0x7fffffffu);
+  if (mx >= 0x7f800000u) *nonfinite = 1;
+}
+
+int launch_nonfinite_scan(const float* p, size_t n, int* flag, cudaStream_t st) {
+  if (n == 0 || !flag) return 0;
+  if ((((uintptr_t)p) & 15) != 0) B200_FAIL(B200_EINVAL, "non-finite scan: input must be 16-byte aligned");
+  nonfinite_scan_kernel<<<grid_for((long long)(n / 4 + 1), kThreads, 148 * 8), kThreads, 0, st>>>(p, n, flag);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_nchw_to_s2d(const float* src, int N, int C, int H, int W, float* dst, cudaStream_t st, int* nonfinite) {
   const long long pixels = (long long)N * (H / 2) * (W / 2);
   if (pixels == 0 || C == 0) return 0;
   if (C == 3 && (((uintptr_t)src) & 7) == 0 && (((uintptr_t)dst) & 15) == 0) {   // W even: every row pair is 8-byte aligned
-    nchw_to_s2d_fixed_kernel<3><<<grid_for(pixels, kThreads, 148 * 32), kThreads, 0, st>>>(src, dst, H, W, pixels);
+    nchw_to_s2d_fixed_kernel<3><<<grid_for(pixels, kThreads, 148 * 32), kThreads, 0, st>>>(src, dst, H, W, pixels, nonfinite);
     B200_CUDA(cudaGetLastError());
     return 0;
   }
+  if (nonfinite) B200_TRY(launch_nonfinite_scan(src, (size_t)N * C * H * W, nonfinite, st));
   nchw_to_s2d_kernel<<<grid_for(pixels * C, kThreads, 148 * 32), kThreads, 0, st>>>(src, dst, C, H, W, pixels);
   B200_CUDA(cudaGetLastError());
   return 0;

@@ -60,6 +60,7 @@ struct StemArgs {
   const float* add;      // [8] or null (folded Add, add_op.rs:75)
   float* p1;             // [N][IMG_FLOATS], halo and tail pre-zeroed, interior written here
   int N;
+  int* nonfinite;        // set to 1 when the input holds an Inf / NaN (or null)
 };
 
 __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const StemArgs a) {
@@ -77,13 +78,16 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const Stem
     const int img0 = g * G;
     const int nimg = min(G, a.N - img0);
     const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)img0 * (IN_HW * IN_HW));
+    uint32_t mx = 0;
     for (int i = tid; i < nimg * 196; i += STEM_THREADS) {
       const float4 v = __ldg(src + i);
+      mx = max(max(mx, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu, max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
       const int im = i / 196, q = i - im * 196, r = q / 7, c4 = q - r * 7;
       float* d = &tile[im][(r + 2) * TILE_W + 2 + c4 * 4];   // 8-byte aligned
       *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
       *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
     }
+    if (a.nonfinite && mx >= 0x7f800000u) *a.nonfinite = 1;
     __syncthreads();
     // ---- 7 passes: task = (image, pooled pixel)
 #pragma unroll 1
@@ -403,9 +407,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
 // ------------------------------------------------------------------------------------------------ host side
 size_t mnist8_p1_floats(int N) { return (size_t)((N + G - 1) / G) * G * IMG_FLOATS; }
 
-int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st) {
+int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st, int* nonfinite) {
   if (N <= 0) return 0;
-  StemArgs a{x, w, bias, add, p1, N};
+  StemArgs a{x, w, bias, add, p1, N, nonfinite};
   const int groups = (N + G - 1) / G;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -67,7 +67,8 @@ struct Plan {
   int in_c0 = 0, in_h0 = 0, in_w0 = 0;   // logical C, H, W of the graph input (in_s2d)
   // Fused small-CNN path (mnist8_fused.cu): the first launch reads the caller's NCHW input directly, so it replaces the
   // input transform (its pointer is per call: outside the CUDA graph, like the transform)
-  std::function<int(const float*, cudaStream_t)> in_stem;
+  std::function<int(const float*, cudaStream_t, int*)> in_stem;   // (input, stream, non-finite flag or null)
+  bool safe = false;        // the finite guard's fallback plan
   float* out_ptr = nullptr; // dense [batch, out_per_image]
   int64_t out_per_image = 0;
   bool out_needs_nchw = false;
@@ -112,6 +113,14 @@ struct b200_model {
   } slots[2];
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint64_t seq = 0;
+  // Finite guard.  The split-precision tensor-core path (x = hi + lo: Inf - Inf = NaN) and the zero-weight fusions (Fire
+  // expand fusion, space-to-depth stem: 0 * Inf = NaN) are exact for FINITE activations only, where the reference
+  // (convolution_op.rs:480 multiplies real taps only) keeps Inf / NaN local.  The input stage of every run raises this
+  // device flag when the input holds an Inf / NaN; the synchronous host entry then reruns the batch on the fallback plan
+  // (CUDA-core fp32 convolutions, no fusions: the reference's semantics), the asynchronous entries report it at sync.
+  int* d_nonfinite = nullptr;
+  int* h_nonfinite = nullptr;   // pinned
+  int opt_finite_guard = 1;
   ~b200_model() {
     if (stage_in) cudaFree(stage_in);
     if (stage_out) cudaFree(stage_out);
@@ -125,6 +134,8 @@ struct b200_model {
     }
     if (h2d) cudaStreamDestroy(h2d);
     if (d2h) cudaStreamDestroy(d2h);
+    if (d_nonfinite) cudaFree(d_nonfinite);
+    if (h_nonfinite) cudaFreeHost(h_nonfinite);
   }
 };
 
@@ -178,6 +189,8 @@ struct Planner {
   b200_model* m;
   Plan* plan;
   int64_t B;
+  bool safe = false;   // the finite guard's fallback plan: CUDA-core fp32 convolutions, no zero-weight fusions
+  int conv_path() const { return safe ? 1 : m->opt_conv_path; }
   std::map<std::string, Val> env;
   std::map<std::string, int> n_consumers;
   std::map<std::string, std::pair<std::string, int>> redirect;  // value -> (concat output, channel offset)
@@ -428,7 +441,7 @@ int Planner::do_conv(size_t i) {
   // 3x3 convolution whose first M1 filters are the 1x1 weights at the centre tap and exact zeros elsewhere: the
   // tcgen05 kernel pays per MMA instruction, not per channel, below 128 channels, so the 1x1 branch rides along for
   // ~8 % of the 3x3 branch's time instead of a launch of its own.  Adding 0 * x terms is exact for finite x.
-  if (m->opt_fire_fusion && m->opt_conv_path != 1 && !chan_add && KH == 1 && KW == 1 && p.strides[0] == 1 && p.strides[1] == 1 &&
+  if (m->opt_fire_fusion && conv_path() != 1 && !chan_add && KH == 1 && KW == 1 && p.strides[0] == 1 && p.strides[1] == 1 &&
       g.pt == 0 && g.pl == 0 && g.Ho == (int)x->dims[2] && g.Wo == (int)x->dims[3] && Ceff % 4 == 0) {
     auto r1 = redirect.find(out_name);
     if (r1 != redirect.end() && r1->second.second == 0) {
@@ -563,7 +576,7 @@ int Planner::do_conv(size_t i) {
   const double bytes = 4.0 * ((double)x->v.pixels() * C + P * M + (double)M * C * KH * KW);
   bool use_tc = false;
   std::shared_ptr<TcWeights> tcw;
-  if (m->opt_conv_path != 1 && tc_supported(a) == 0) {
+  if (conv_path() != 1 && tc_supported(a) == 0) {
     use_tc = true;
     if (!dry) {
       std::string key = "tc:" + w->init->name + ":" + std::to_string(Ceff) + (x->s2d ? ":s2d" : "");
@@ -573,7 +586,7 @@ int Planner::do_conv(size_t i) {
         m->tc_weights[key] = tcw;
       } else tcw = it->second;
     }
-  } else if (m->opt_conv_path == 2) {
+  } else if (conv_path() == 2) {
     B200_FAIL(B200_EUNSUPPORTED, "Conv %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
   }
   if (use_tc) add_step(label, "conv_tc", flops, bytes, [a, tcw](cudaStream_t st) { return launch_conv_tc(a, *tcw, st); });
@@ -758,7 +771,7 @@ int Planner::do_matmul(size_t i) {
   c.reverse = next_reverse();
   // mul_op.rs:23 on the convolution's tcgen05 path: rows are the "pixels" of a pointwise layer (TMA-fed A tiles), the
   // N columns one channel tile (MNIST: 10 -> BN = 16)
-  if (m->opt_conv_path != 1 && tc_supported(c) == 0) {
+  if (conv_path() != 1 && tc_supported(c) == 0) {
     std::shared_ptr<TcWeights> tcw;
     if (!dry) {
       auto it = m->tc_weights.find("tc:" + key);
@@ -770,7 +783,7 @@ int Planner::do_matmul(size_t i) {
     add_step(label, "matmul_tc", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
              [c, tcw](cudaStream_t st) { return launch_conv_tc(c, *tcw, st); });
   } else {
-    if (m->opt_conv_path == 2) B200_FAIL(B200_EUNSUPPORTED, "MatMul %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
+    if (conv_path() == 2) B200_FAIL(B200_EUNSUPPORTED, "MatMul %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
     add_step(label, "matmul_simt", 2.0 * R * K * N, 4.0 * (R * K + R * N + (double)K * N),
              [c](cudaStream_t st) { return launch_conv_simt(c, st); });
   }
@@ -798,7 +811,7 @@ int Planner::matmul_weights(const Val& b, int perm_C, int perm_HW, int K, int N,
 // Everything else keeps the node-by-node plan.  (BASELINE.json config 5; kernels and layout in mnist8_fused.cu.)
 int Planner::try_plan_mnist8(bool* done) {
   *done = false;
-  if (!m->opt_fused_cnn || m->opt_conv_path == 1) return 0;
+  if (!m->opt_fused_cnn || conv_path() == 1) return 0;
   if (m->in_dims[1] != 1 || m->in_dims[2] != 28 || m->in_dims[3] != 28 || (m->in_dims[0] != 1 && m->in_dims[0] > 0)) return 0;
   auto next = [&](const std::string& v, const char* op, size_t* idx) -> const WireNode* {
     const WireNode* c = sole_consumer(v, idx);
@@ -909,7 +922,7 @@ int Planner::try_plan_mnist8(bool* done) {
   }
   // the halo (and the 64 pad bytes per image) of the stem output are zero for the plan's lifetime: nothing else writes them
   B200_CUDA(cudaMemsetAsync(p1, 0, mnist8_p1_floats(N) * sizeof(float), m->ctx->stream));
-  plan->in_stem = [=](const float* d_in, cudaStream_t st) { return launch_mnist8_stem(d_in, dw1, db1, da1, p1, N, st); };
+  plan->in_stem = [=](const float* d_in, cudaStream_t st, int* flag) { return launch_mnist8_stem(d_in, dw1, db1, da1, p1, N, st, flag); };
   float* dout = y.v.p;
   // the reference's FLOPs for these nodes (1.573 MFLOP per image with the stem's 0.314); the 52 conv2 outputs per image
   // that MaxPool 3x3/3 floors away are not computed here
@@ -1014,7 +1027,7 @@ int Planner::run() {
   // channel-padded layout, seven k-blocks), 12 channels are three 16-byte chunks per tap, and the transform writes
   // 25 % fewer bytes.  Exact: the extra taps have zero weights.
   plan->in_s2d = false;
-  if (m->opt_s2d && m->opt_conv_path != 1 && in.v.C >= 1 && (4 * in.v.C) % 4 == 0 && in.v.H % 2 == 0 && in.v.W % 2 == 0) {
+  if (m->opt_s2d && conv_path() != 1 && in.v.C >= 1 && (4 * in.v.C) % 4 == 0 && in.v.H % 2 == 0 && in.v.W % 2 == 0) {
     size_t jc = 0;
     const WireNode* c = sole_consumer(m->input_name, &jc);
     const WireTensor* w = (c && c->op_type == "Conv" && c->input.size() >= 2 && c->input[0] == m->input_name) ? m->wm.find_initializer(c->input[1]) : nullptr;
@@ -1145,14 +1158,16 @@ int Planner::run() {
   return 0;
 }
 
-int build_plan(b200_model* m, int64_t batch, Plan** out) {
-  auto it = m->plans.find(batch);
-  if (it != m->plans.end()) { *out = it->second.get(); return 0; }
+int build_plan(b200_model* m, int64_t batch, Plan** out, bool safe = false) {
   if (batch <= 0) B200_FAIL(B200_EINVAL, "batch must be positive");
+  const int64_t key = safe ? -batch : batch;
+  auto it = m->plans.find(key);
+  if (it != m->plans.end()) { *out = it->second.get(); return 0; }
   std::unique_ptr<Plan> plan(new Plan());
   plan->batch = batch;
+  plan->safe = safe;
   Planner pl;
-  pl.m = m; pl.plan = plan.get(); pl.B = batch;
+  pl.m = m; pl.plan = plan.get(); pl.B = batch; pl.safe = safe;
   pl.dry = true;
   B200_TRY(pl.run());
   plan->arena.reset(new DevBuf());
@@ -1166,7 +1181,7 @@ int build_plan(b200_model* m, int64_t batch, Plan** out) {
   B200_TRY(pl.run());
   B200_CUDA(cudaStreamSynchronize(m->ctx->stream));  // constant uploads / weight preparation done
   *out = plan.get();
-  m->plans[batch] = std::move(plan);
+  m->plans[key] = std::move(plan);
   return 0;
 }
 
@@ -1183,15 +1198,18 @@ int run_steps(b200_model* m, Plan* plan, cudaStream_t st) {
 int run_plan(b200_model* m, Plan* plan, const float* d_in, float* d_out, cudaEvent_t input_consumed = nullptr) {
   cudaStream_t st = m->ctx->stream;
   // 1. input: logical NCHW (what the reference's manage_input_data holds, utils.rs:29-45) -> channels-last rows
+  int* flag = (m->opt_finite_guard && !plan->safe) ? m->d_nonfinite : nullptr;
   if (plan->in_stem) {
-    B200_TRY(plan->in_stem(d_in, st));
+    B200_TRY(plan->in_stem(d_in, st, flag));
     m->ctx->launches++;
   } else if (plan->in_direct) {
+    if (flag) { B200_TRY(launch_nonfinite_scan(d_in, (size_t)plan->in_view.numel(), flag, st)); m->ctx->launches++; }
     B200_CUDA(cudaMemcpyAsync(plan->in_view.p, d_in, (size_t)plan->in_view.numel() * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else if (plan->in_s2d) {
-    B200_TRY(launch_nchw_to_s2d(d_in, plan->in_view.N, plan->in_c0, plan->in_h0, plan->in_w0, plan->in_view.p, st));
+    B200_TRY(launch_nchw_to_s2d(d_in, plan->in_view.N, plan->in_c0, plan->in_h0, plan->in_w0, plan->in_view.p, st, flag));
     m->ctx->launches++;
   } else {
+    if (flag) { B200_TRY(launch_nonfinite_scan(d_in, (size_t)plan->batch * m->in_dims[0] * m->in_dims[1] * m->in_dims[2] * m->in_dims[3], flag, st)); m->ctx->launches++; }
     B200_TRY(launch_nchw_to_rows(d_in, plan->in_view, plan->in_zero_pad, st));
     m->ctx->launches++;
   }
@@ -1246,6 +1264,10 @@ int b200_model_load_onnx(b200_ctx* ctx, const uint8_t* bytes, size_t len, b200_m
   }
   if (found != 1) B200_FAIL(B200_EUNSUPPORTED, "expected exactly one non-initializer graph input, found %d", found);
   Guard g(ctx);
+  B200_CUDA(cudaMalloc((void**)&m->d_nonfinite, sizeof(int)));
+  B200_CUDA(cudaMemsetAsync(m->d_nonfinite, 0, sizeof(int), ctx->stream));
+  B200_CUDA(cudaHostAlloc((void**)&m->h_nonfinite, sizeof(int), cudaHostAllocDefault));
+  *m->h_nonfinite = 0;
   Plan* p = nullptr;
   B200_TRY(build_plan(m.get(), 1, &p));  // validates every node up front (unknown op / attribute errors surface here)
   m->out_per_image = p->out_per_image;
@@ -1304,7 +1326,8 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
   } else if (k == "fused_cnn") {
     if (m->opt_fused_cnn != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_fused_cnn = value ? 1 : 0;
-  } else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
+  } else if (k == "finite_guard") m->opt_finite_guard = value ? 1 : 0;
+  else if (k == "verbose") m->opt_verbose = value ? 1 : 0;
   else B200_FAIL(B200_EINVAL, "unknown option %s", key);
   return 0;
 }
@@ -1340,7 +1363,19 @@ int b200_model_run(b200_model* m, const float* host_in, int64_t batch, float* ho
   B200_CUDA(cudaMemcpyAsync(m->stage_in, host_in, in_bytes, cudaMemcpyHostToDevice, st));
   B200_TRY(run_plan(m, p, m->stage_in, m->stage_out));
   B200_CUDA(cudaMemcpyAsync(host_out, m->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaMemcpyAsync(m->h_nonfinite, m->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  if (*m->h_nonfinite) {
+    // finite guard: the input holds an Inf / NaN -- rerun on the fallback plan, whose arithmetic keeps them where the
+    // reference keeps them (CUDA-core fp32, real taps only)
+    *m->h_nonfinite = 0;
+    B200_CUDA(cudaMemsetAsync(m->d_nonfinite, 0, sizeof(int), st));
+    Plan* ps = nullptr;
+    B200_TRY(build_plan(m, batch, &ps, /*safe=*/true));
+    B200_TRY(run_plan(m, ps, m->stage_in, m->stage_out));
+    B200_CUDA(cudaMemcpyAsync(host_out, m->stage_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 
@@ -1401,6 +1436,16 @@ int b200_model_sync(b200_model* m) {
   B200_CUDA(cudaStreamSynchronize(m->ctx->stream));
   if (m->h2d) B200_CUDA(cudaStreamSynchronize(m->h2d));
   if (m->d2h) B200_CUDA(cudaStreamSynchronize(m->d2h));
+  if (m->opt_finite_guard) {
+    B200_CUDA(cudaMemcpy(m->h_nonfinite, m->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*m->h_nonfinite) {
+      *m->h_nonfinite = 0;
+      B200_CUDA(cudaMemset(m->d_nonfinite, 0, sizeof(int)));
+      B200_FAIL(B200_EUNSUPPORTED, "a batch run through b200_model_run_async / b200_model_run_device since the last sync held an Inf or NaN input: the "
+                "split-precision tensor-core path is exact for finite data only -- rerun that batch through b200_model_run (it falls back to the "
+                "CUDA-core fp32 plan by itself) or set the option conv_path=1");
+    }
+  }
   return 0;
 }
 
@@ -1476,7 +1521,7 @@ int b200_model_profile(b200_model* m, int64_t batch, int iters, int flush_l2, ch
       if (cudaMalloc((void**)&scratch, in_floats * sizeof(float)) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc for the profile's scratch input"); }
       cudaMemsetAsync(scratch, 0, in_floats * sizeof(float), st);
       auto stage = [&]() -> int {
-        if (p->in_stem) return p->in_stem(scratch, st);
+        if (p->in_stem) return p->in_stem(scratch, st, nullptr);
         if (p->in_s2d) return launch_nchw_to_s2d(scratch, p->in_view.N, p->in_c0, p->in_h0, p->in_w0, p->in_view.p, st);
         return launch_nchw_to_rows(scratch, p->in_view, p->in_zero_pad, st);
       };

@@ -178,6 +178,55 @@ def test_fire_module_alone(ctx, tmp_path, cin, squeeze, expand, hw, batch, fuses
     assert np.array_equal(eng(xs), fused), "tile walking direction must not change the bits"
 
 
+def _assert_same_with_nonfinite(got, want, what):
+    got = np.asarray(got); want = np.asarray(want)
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN pattern differs ({int(np.isnan(got).sum())} vs {int(np.isnan(want).sum())})"
+    inf = np.isinf(want)
+    assert np.array_equal(np.isinf(got), inf) and np.array_equal(got[inf], want[inf]), f"{what}: Inf pattern differs"
+    fin = np.isfinite(want)
+    assert_close(got[fin], want[fin], what)
+
+
+def test_nonfinite_inputs_follow_the_reference(ctx, tmp_path, synth_onnx):
+    """An Inf and a NaN reaching the squeeze output of a Fire module: the reference multiplies real taps only
+    (convolution_op.rs:480), so they stay local to the outputs that read them (the 1x1 expand of a neighbouring pixel stays
+    finite).  The tensor-core path cannot do that (hi / lo split: Inf - Inf = NaN; the Fire expand fusion adds 0 * x
+    terms), so the run's input stage detects non-finite input and b200_model_run falls back to the CUDA-core fp32 plan by
+    itself; the asynchronous entries report it at b200_model_sync."""
+    import torch
+    from onnx_rusty_inference_engine_b200 import _lib as L, synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    path = str(tmp_path / "fire.onnx")
+    with open(path, "wb") as f:
+        f.write(synth.build_fire(8, 16, 64, 17, seed=3))          # fire2-like: the expand fusion applies
+    xs = synth.synthetic_batch(3, chw=(8, 17, 17), seed=4, std=1.0)
+    xs[0, 2, 5, 6] = np.inf
+    xs[1, 0, 9, 9] = np.nan
+    with np.errstate(all="ignore"):
+        want = rm.run_batch(ow.load_model(path), xs, threads=2)
+    assert np.isinf(want).any() and not np.isnan(want).any()      # upstream's Relu (f32::max) turns a NaN into 0
+    eng = Engine(path, ctx=ctx)
+    got = eng(xs)                                                  # guard trips -> fallback plan
+    _assert_same_with_nonfinite(got.reshape(want.shape), want, "fire module with Inf / NaN input")
+    clean = synth.synthetic_batch(3, chw=(8, 17, 17), seed=4, std=1.0)
+    assert np.isfinite(eng(clean)).all(), "the guard must reset after a non-finite batch"
+    # asynchronous entry: reported at sync, then cleared
+    xh = torch.from_numpy(xs).pin_memory(); oh = torch.empty((3, eng.out_per_image)).pin_memory()
+    eng.run_pinned_async(xh, oh)
+    with pytest.raises(L.B200Error, match="Inf or NaN"):
+        eng.sync()
+    eng.run_pinned_async(torch.from_numpy(clean).pin_memory(), oh)
+    eng.sync()
+    # the whole network (space-to-depth stem + Fire fusions): same contract
+    big = synth.synthetic_batch(2, seed=21)
+    big[1, 1, 100, 37] = -np.inf
+    with np.errstate(all="ignore"):
+        want_big = rm.run_batch(ow.load_model(synth_onnx), big, threads=2)
+    _assert_same_with_nonfinite(Engine(synth_onnx, ctx=ctx)(big), want_big, "SqueezeNet with an Inf input pixel")
+
+
 def test_space_to_depth_stem_matches_plain_layout(ctx, synth_onnx):
     """conv1 (7x7 / 2 on 3 channels) on the 2x2 space-to-depth copy of the input (a 4x4 / 1 convolution over 12 channels with
     zero-padded weights) against the plain channel-padded layout and the oracle."""
