@@ -28,6 +28,23 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert L.lib().b200_version().startswith(b"b200rt")
 
 
+def test_rust_sys_crate_names_exactly_the_header_symbols():
+    """rust/b200rt-sys/src/lib.rs is generated from the header (tools/gen_b200rt_sys.py; no Rust toolchain here to compile
+    it): it must be up to date and declare every exported symbol, and the wrapper crate keeps the reference's ten op names."""
+    import subprocess, sys
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_b200rt_sys.py")], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(ROOT, "rust", "b200rt-sys", "src", "lib.rs")) as f:
+        committed = f.read()
+    assert committed == gen, "rust/b200rt-sys/src/lib.rs is stale: python tools/gen_b200rt_sys.py > rust/b200rt-sys/src/lib.rs"
+    assert sorted(set(re.findall(r"pub fn (b200_[a-z0-9_]+)\(", committed))) == _declared_symbols()
+    ops = os.path.join(ROOT, "rust", "onnx-rusty-inference-engine-b200", "src", "inference_fp32_ops")
+    for mod, fn in (("convolution_op", "convolution"), ("max_pool_op", "max_pool"), ("relu_op", "relu"), ("add_op", "add"), ("mul_op", "mul"),
+                    ("reshape_op", "reshape"), ("concatenate_op", "concatenation"), ("dropout_op", "drop_out"),
+                    ("global_average_pool_op", "global_average_pool"), ("softmax_op", "softmax")):
+        with open(os.path.join(ops, mod + ".rs")) as f:
+            assert f"pub fn {fn}(output_container: &Store" in f.read(), (mod, fn)
+
+
 def test_no_cpu_fallback():
     if L.lib().b200_device_count() > 0:
         pytest.skip("a B200 is present")
