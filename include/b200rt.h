@@ -187,6 +187,10 @@ int b200_model_set_option(b200_model *m, const char *key, int64_t value);
  * before every timed launch (cold cache), 2 = run the whole launch list in model order `iters` times and time every
  * launch in place (the cache state of a real run).  Format: [{"name":..,"kind":..,"ms":..,"flops":..,"bytes":..}, ...]. */
 int b200_model_profile(b200_model *m, int64_t batch, int iters, int flush_l2, char *buf, size_t cap);
+/* HBM held by the activation arena planned for `batch` images: with liveness reuse (activations whose launch ranges are
+ * disjoint share bytes) and, for comparison, the sum of all activations (what the store of model_inference.rs:30-32, which
+ * frees nothing until inference() returns, would hold). */
+int b200_model_arena_bytes(b200_model *m, int64_t batch, int64_t *arena_bytes, int64_t *no_reuse_bytes);
 /* Number of kernel launches one b200_model_run_device of `batch` images issues. */
 int64_t b200_model_launches_per_run(b200_model *m, int64_t batch);
 

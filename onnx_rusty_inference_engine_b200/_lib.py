@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200_model_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "b200_model_profile": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "b200_model_launches_per_run": (C.c_int64, [_vp, C.c_int64]),
+    "b200_model_arena_bytes": (C.c_int, [_vp, C.c_int64, _i64p, _i64p]),
     "b200_tensorproto_read": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, _i64p, C.POINTER(C.c_int),
                                         C.POINTER(C.c_size_t)]),
 }
@@ -328,6 +329,12 @@ class Model:
 
     def sync(self) -> None:
         check(lib().b200_model_sync(self._h))
+
+    def arena_bytes(self, batch: int):
+        """(bytes of the liveness-coloured activation arena, bytes without reuse) for a batch size."""
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().b200_model_arena_bytes(self._h, int(batch), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def launches_per_run(self, batch: int) -> int:
         return int(lib().b200_model_launches_per_run(self._h, int(batch)))

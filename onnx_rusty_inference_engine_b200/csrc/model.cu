@@ -39,6 +39,7 @@ struct Val {  // one graph value for the planned batch
   int64_t dims[4] = {0, 0, 0, 0};  // logical, dims[0] already scaled to the batch
   TView v;
   bool planned = false;      // has a device location
+  int alloc = -1;            // arena allocation that backs it (liveness tracking); aliases and channel views share it
   bool pad_zeroed = false;   // lanes [C, ld) are zero
   bool s2d = false;          // graph input stored 2x2 space-to-depth: v is [N, H/2, W/2, 4*C], channel (dy*2+dx)*C + c
   bool is_init = false;      // initializer (constant)
@@ -59,7 +60,9 @@ struct Plan {
   int64_t batch = 0;
   std::vector<Step> steps;
   std::unique_ptr<DevBuf> arena;
-  size_t arena_used = 0;
+  size_t arena_used = 0;    // bytes of the coloured arena
+  size_t arena_bump = 0;    // sum of all allocations (no reuse)
+  uint64_t last_used = 0;   // LRU stamp (b200_model::use_counter)
   TView in_view;            // where the input transform writes
   bool in_zero_pad = false;
   bool in_direct = false;   // input needs no transform (C == 1 or H*W == 1): memcpy
@@ -113,6 +116,7 @@ struct b200_model {
   } slots[2];
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint64_t seq = 0;
+  uint64_t use_counter = 0;   // LRU stamps of `plans`
   // Finite guard.  The split-precision tensor-core path (x = hi + lo: Inf - Inf = NaN) and the zero-weight fusions (Fire
   // expand fusion, space-to-depth stem: 0 * Inf = NaN) are exact for FINITE activations only, where the reference
   // (convolution_op.rs:480 multiplies real taps only) keeps Inf / NaN local.  The input stage of every run raises this
@@ -195,17 +199,54 @@ struct Planner {
   std::map<std::string, int> n_consumers;
   std::map<std::string, std::pair<std::string, int>> redirect;  // value -> (concat output, channel offset)
   std::set<size_t> consumed;                                    // node indices folded into an earlier step
-  std::vector<std::pair<size_t, size_t>> arena_allocs;
-
-  // ----- arena: plain bump allocation, 256-byte aligned, sized in a dry pass then materialised
-  size_t arena_cursor = 0;
+  // ----- arena with liveness reuse.  The dry pass records every allocation with the launch that
+  // first writes it (def) and the last launch that reads it (last); offsets then come from a first-fit interval
+  // colouring: two allocations may share bytes iff their [def, last] launch ranges are disjoint (one in-order stream, so
+  // a launch never sees a buffer whose last reader has not finished; an output never aliases an input of its own
+  // launch).  The second pass hands out the same allocations in the same order at their coloured offsets.
+  struct ArenaRec { size_t bytes; int def, last; size_t off; };
+  std::vector<ArenaRec> recs;
+  size_t alloc_seq = 0;
+  size_t arena_cursor = 0;   // dry pass: sum of all allocations (what a bump allocator would need); then the coloured size
   bool dry = true;
-  float* arena_alloc(size_t floats) {
-    size_t bytes = (floats * sizeof(float) + 255) & ~(size_t)255;
-    size_t off = arena_cursor;
-    arena_cursor += bytes;
-    if (dry) return nullptr;
-    return (float*)((char*)plan->arena->p + off);
+  static constexpr int LIVE_FOREVER = 0x7fffffff;
+  float* arena_alloc(size_t floats, int* id = nullptr, bool forever = false) {
+    const size_t bytes = (floats * sizeof(float) + 255) & ~(size_t)255;
+    const size_t i = alloc_seq++;
+    if (id) *id = (int)i;
+    if (dry) {
+      recs.push_back(ArenaRec{bytes, (int)step_counter, forever ? LIVE_FOREVER : (int)step_counter, 0});
+      arena_cursor += bytes;
+      return nullptr;
+    }
+    return (float*)((char*)plan->arena->p + recs[i].off);
+  }
+  void touch(const Val* v) {   // v is read by the launch being planned
+    if (dry && v && v->alloc >= 0 && recs[(size_t)v->alloc].last < (int)step_counter) recs[(size_t)v->alloc].last = (int)step_counter;
+  }
+  void keep_forever(int alloc) { if (dry && alloc >= 0) recs[(size_t)alloc].last = LIVE_FOREVER; }
+  size_t colour() {
+    size_t top = 0;
+    std::vector<size_t> order(recs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return recs[a].bytes > recs[b].bytes; });   // big first
+    std::vector<size_t> placed;
+    for (size_t i : order) {
+      // candidate offsets: 0 and the end of every conflicting allocation already placed; take the lowest that fits
+      std::vector<std::pair<size_t, size_t>> busy;   // [begin, end) of conflicting allocations
+      for (size_t j : placed)
+        if (!(recs[j].last < recs[i].def || recs[i].last < recs[j].def)) busy.push_back({recs[j].off, recs[j].off + recs[j].bytes});
+      std::sort(busy.begin(), busy.end());
+      size_t off = 0;
+      for (auto& b : busy) {
+        if (off + recs[i].bytes <= b.first) break;
+        if (b.second > off) off = b.second;
+      }
+      recs[i].off = off;
+      placed.push_back(i);
+      top = std::max(top, off + recs[i].bytes);
+    }
+    return top;
   }
 
   const WireNode* sole_consumer(const std::string& value, size_t* idx) {
@@ -219,7 +260,7 @@ struct Planner {
 
   Val* get(const std::string& name) {
     auto it = env.find(name);
-    if (it != env.end()) return &it->second;
+    if (it != env.end()) { touch(&it->second); return &it->second; }
     const WireTensor* t = m->wm.find_initializer(name);
     if (!t) return nullptr;
     Val v;
@@ -242,18 +283,19 @@ struct Planner {
           parent->v.N = (int)parent->dims[0]; parent->v.C = (int)parent->dims[1];
           parent->v.H = (int)parent->dims[2]; parent->v.W = (int)parent->dims[3];
           parent->v.ld = parent->v.C;
-          parent->v.p = arena_alloc((size_t)parent->v.pixels() * parent->v.ld);
+          parent->v.p = arena_alloc((size_t)parent->v.pixels() * parent->v.ld, &parent->alloc);
           parent->planned = true;
         }
+        v->alloc = parent->alloc;
         v->v.ld = parent->v.ld;
         v->v.p = dry ? nullptr : parent->v.p + r->second.second;
       } else {
         v->v.ld = v->v.C;
-        v->v.p = arena_alloc((size_t)v->v.pixels() * v->v.ld);
+        v->v.p = arena_alloc((size_t)v->v.pixels() * v->v.ld, &v->alloc);
       }
     } else {
       v->v.N = (int)v->dims[0]; v->v.C = (int)v->dims[1]; v->v.H = v->v.W = 1; v->v.ld = v->v.C;
-      v->v.p = arena_alloc((size_t)v->v.numel());
+      v->v.p = arena_alloc((size_t)v->v.numel(), &v->alloc);
     }
     v->planned = true;
     return 0;
@@ -716,6 +758,7 @@ int Planner::do_reshape(size_t i) {
   }
   if (order_free || fold) {
     y.v.p = x->v.p; y.v.N = (int)y.dims[0]; y.v.C = (int)y.dims[1]; y.v.H = y.v.W = 1; y.v.ld = y.v.C;
+    y.alloc = x->alloc;
     y.planned = true;
     if (fold) { y.perm_C = x->v.C; y.perm_HW = x->v.H * x->v.W; }
   } else {
@@ -905,7 +948,7 @@ int Planner::try_plan_mnist8(bool* done) {
   B200_TRY(matmul_weights(*bval, 16, 16, 256, 10, "matw:" + mm->input[1] + ":16x16", &dwm));
   if (bm) B200_TRY(vec_const(*bm, 10, &dbm));
   const int N = (int)B;
-  float* p1 = arena_alloc(mnist8_p1_floats(N));
+  float* p1 = arena_alloc(mnist8_p1_floats(N), nullptr, /*forever=*/true);   // its zero halo must survive: never shared
   Val y; y.rank = 2; y.dims[0] = B; y.dims[1] = 10;
   B200_TRY(place(out_name, &y));
   for (size_t k : used) consumed.insert(k);
@@ -1011,7 +1054,8 @@ int Planner::do_softmax(size_t i) {
 }
 
 int Planner::run() {
-  env.clear(); consumed.clear(); arena_cursor = 0; arena_allocs.clear(); step_counter = 0;
+  env.clear(); consumed.clear(); alloc_seq = 0; step_counter = 0;
+  if (dry) { recs.clear(); arena_cursor = 0; }
   n_consumers.clear();
   for (auto& n : m->wm.nodes) for (auto& in : n.input) n_consumers[in]++;
   redirect.clear();
@@ -1044,7 +1088,7 @@ int Planner::run() {
       }
     }
   }
-  in.v.p = arena_alloc((size_t)in.v.pixels() * in.v.ld);
+  in.v.p = arena_alloc((size_t)in.v.pixels() * in.v.ld, &in.alloc);
   in.planned = true; in.pad_zeroed = true;
   env[m->input_name] = in;
   plan->in_view = in.v;
@@ -1139,14 +1183,17 @@ int Planner::run() {
     if (it == env.end() || !it->second.planned) B200_FAIL(B200_EINVAL, "graph output %s was not produced", out_name.c_str());
   }
   Val& o = it->second;
+  ++step_counter;            // the result outlives every launch (read by the caller after the run)
+  touch(&o);
+  keep_forever(o.alloc);
   plan->out_per_image = o.v.numel() / std::max<int64_t>(1, B);
   plan->out_view = o.v;
   if (o.rank == 4 && o.v.H * o.v.W > 1 && o.v.C > 1) {
     plan->out_needs_nchw = true;
-    plan->out_ptr = arena_alloc((size_t)o.v.numel());
+    plan->out_ptr = arena_alloc((size_t)o.v.numel(), nullptr, true);
   } else if (!o.v.dense()) {
     plan->out_needs_nchw = true;  // strided rows -> dense copy via the same kernel (HW == 1 or C == 1)
-    plan->out_ptr = arena_alloc((size_t)o.v.numel());
+    plan->out_ptr = arena_alloc((size_t)o.v.numel(), nullptr, true);
   } else {
     plan->out_needs_nchw = false;
     plan->out_ptr = o.v.p;
@@ -1162,7 +1209,20 @@ int build_plan(b200_model* m, int64_t batch, Plan** out, bool safe = false) {
   if (batch <= 0) B200_FAIL(B200_EINVAL, "batch must be positive");
   const int64_t key = safe ? -batch : batch;
   auto it = m->plans.find(key);
-  if (it != m->plans.end()) { *out = it->second.get(); return 0; }
+  if (it != m->plans.end()) { it->second->last_used = ++m->use_counter; *out = it->second.get(); return 0; }
+  // one arena per planned batch size: keep the most recently used few (a server that sees many batch sizes must not
+  // accumulate arenas); kernels of an evicted plan may still be in flight, so drain the streams first
+  constexpr size_t MAX_PLANS = 6;
+  if (m->plans.size() >= MAX_PLANS) {
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->h2d) cudaStreamSynchronize(m->h2d);
+    if (m->d2h) cudaStreamSynchronize(m->d2h);
+    while (m->plans.size() >= MAX_PLANS) {
+      auto lru = m->plans.begin();
+      for (auto p = m->plans.begin(); p != m->plans.end(); ++p) if (p->second->last_used < lru->second->last_used) lru = p;
+      m->plans.erase(lru);
+    }
+  }
   std::unique_ptr<Plan> plan(new Plan());
   plan->batch = batch;
   plan->safe = safe;
@@ -1170,16 +1230,19 @@ int build_plan(b200_model* m, int64_t batch, Plan** out, bool safe = false) {
   pl.m = m; pl.plan = plan.get(); pl.B = batch; pl.safe = safe;
   pl.dry = true;
   B200_TRY(pl.run());
+  plan->arena_bump = pl.arena_cursor;         // what a bump allocator (round 1) would have taken
+  const size_t coloured = pl.colour();
   plan->arena.reset(new DevBuf());
-  plan->arena->bytes = pl.arena_cursor + 256;
+  plan->arena->bytes = coloured + 256;
   if (cudaMalloc((void**)&plan->arena->p, plan->arena->bytes) != cudaSuccess) {
     cudaGetLastError();
     B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for the activation arena (batch %lld)", plan->arena->bytes, (long long)batch);
   }
-  plan->arena_used = pl.arena_cursor;
+  plan->arena_used = coloured;
   pl.dry = false;
   B200_TRY(pl.run());
   B200_CUDA(cudaStreamSynchronize(m->ctx->stream));  // constant uploads / weight preparation done
+  plan->last_used = ++m->use_counter;
   *out = plan.get();
   m->plans[key] = std::move(plan);
   return 0;
@@ -1483,6 +1546,16 @@ int b200_model_run_sharded(b200_model* const* models, int n, const float* host_i
   for (auto& t : th) t.join();
   for (int i = 0; i < n; ++i)
     if (rcs[(size_t)i]) B200_FAIL(rcs[(size_t)i], "shard %d of %d: %s", i, n, errs[(size_t)i].c_str());
+  return 0;
+}
+
+int b200_model_arena_bytes(b200_model* m, int64_t batch, int64_t* arena_bytes, int64_t* no_reuse_bytes) {
+  if (!m) B200_FAIL(B200_EINVAL, "model is NULL");
+  Guard g(m->ctx);
+  Plan* p = nullptr;
+  B200_TRY(build_plan(m, batch, &p));
+  if (arena_bytes) *arena_bytes = (int64_t)p->arena_used;
+  if (no_reuse_bytes) *no_reuse_bytes = (int64_t)p->arena_bump;
   return 0;
 }
 

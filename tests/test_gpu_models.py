@@ -290,6 +290,42 @@ def test_squeezenet_batch256_sampled_vs_oracle(ctx, synth_onnx):
     assert np.allclose(got.sum(1), 1.0, atol=1e-5) and np.isfinite(got).all()
 
 
+def test_arena_liveness_reuse_and_plan_eviction(ctx, synth_onnx):
+    """SURVEY.md section 8b "arena with liveness reuse": activations whose launch ranges are disjoint share bytes (the reference
+    frees nothing until inference() returns); plans of batch sizes not used recently are evicted.  Results unchanged."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    eng = Engine(synth_onnx, ctx=ctx)
+    arena, bump = eng.model.arena_bytes(256)
+    print(f"arena at batch 256: {arena / 1e9:.2f} GB with reuse, {bump / 1e9:.2f} GB without")
+    # the largest live set is conv1's input + output (0.12 + 1.17 GB) ~ 1.3 GB: demand <= 2x that, and a big cut
+    assert arena <= 2.6e9 and arena < 0.4 * bump
+    xs = synth.synthetic_batch(9, seed=33)
+    first = eng(xs[:3])
+    for b in (1, 2, 4, 5, 6, 7, 8, 9):          # more batch sizes than the plan cache keeps
+        got = eng(xs[:b])
+        assert np.array_equal(got[:min(b, 3)], first[:min(b, 3)]), f"batch {b}"
+    assert np.array_equal(eng(xs[:3]), first), "re-planned after eviction"
+
+
+def test_squeezenet_batch2048_sampled_vs_oracle(synth_onnx):
+    """Config 4's per-GPU worst case on ONE device: batch 2048 (seed 2), 4 images sampled from its output against the oracle."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    xs = synth.synthetic_batch(2048, seed=2)
+    eng = Engine(synth_onnx, device=0)
+    arena, bump = eng.model.arena_bytes(2048)
+    print(f"arena at batch 2048: {arena / 1e9:.2f} GB with reuse, {bump / 1e9:.2f} GB without")
+    got = eng(xs)
+    idx = [0, 777, 1500, 2047]
+    want = rm.run_batch(ow.load_model(synth_onnx), xs[idx], threads=4)
+    assert_close(got[idx], want, "squeezenet batch 2048, sampled images vs oracle")
+    assert (got[idx].argmax(1) == want.argmax(1)).all()
+    assert np.isfinite(got).all()
+    eng.model.close()
+
+
 def test_engine_on_torch_stream(synth_onnx):
     """Device-resident entry (b200_model_run_device) on torch's current stream, input/outputs as torch tensors."""
     import torch
