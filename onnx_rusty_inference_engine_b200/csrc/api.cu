@@ -525,16 +525,25 @@ int b200_reshape(b200_ctx* ctx, const b200_tensor* x, const int64_t* shape, int 
 int b200_concat(b200_ctx* ctx, const b200_tensor* a, const b200_tensor* b, int64_t axis, b200_tensor** y) {
   if (!ctx || !a || !b || !y) B200_FAIL(B200_EINVAL, "NULL argument");
   if (a->rank != 4 || b->rank != 4) B200_FAIL(B200_EINVAL, "Concat inputs must be rank 4 (concatenate_op.rs:15-18)");
-  if (axis != 1) B200_FAIL(B200_EUNSUPPORTED, "Concat: only axis=1 (channels) is implemented; both reference models use it");
-  if (a->dims[0] != b->dims[0] || a->dims[2] != b->dims[2] || a->dims[3] != b->dims[3])
-    B200_FAIL(B200_EINVAL, "Concat: non-axis dims differ");
+  if (axis < 0 || axis > 3) B200_FAIL(B200_EINVAL, "Concat: axis %lld out of range for rank 4 (concatenate_op.rs:31 Axis(axis as usize))", (long long)axis);
+  for (int d = 0; d < 4; ++d)
+    if (d != axis && a->dims[d] != b->dims[d]) B200_FAIL(B200_EINVAL, "Concat: non-axis dims differ (ndarray::concatenate returns Err, unwrapped at concatenate_op.rs:32)");
   Guard gd(ctx);
-  int64_t yd[4] = {a->dims[0], a->dims[1] + b->dims[1], a->dims[2], a->dims[3]};
+  int64_t yd[4] = {a->dims[0], a->dims[1], a->dims[2], a->dims[3]};
+  yd[axis] += b->dims[axis];
   B200_TRY(ensure_out(ctx, y, yd, 4));
-  TView ya = (*y)->v; ya.C = a->v.C;
-  TView yb = (*y)->v; yb.C = b->v.C; yb.p += a->v.C;
-  if (!(a->v.p == ya.p && a->v.ld == ya.ld)) { B200_TRY(launch_copy_rows(a->v, ya, ctx->stream)); ctx->launches++; }
-  if (!(b->v.p == yb.p && b->v.ld == yb.ld)) { B200_TRY(launch_copy_rows(b->v, yb, ctx->stream)); ctx->launches++; }
+  if (axis == 1) {
+    // channels: the inputs may already BE the matching channel views of *y (zero-copy Concat)
+    TView ya = (*y)->v; ya.C = a->v.C;
+    TView yb = (*y)->v; yb.C = b->v.C; yb.p += a->v.C;
+    if (!(a->v.p == ya.p && a->v.ld == ya.ld)) { B200_TRY(launch_copy_rows(a->v, ya, ctx->stream)); ctx->launches++; }
+    if (!(b->v.p == yb.p && b->v.ld == yb.ld)) { B200_TRY(launch_copy_rows(b->v, yb, ctx->stream)); ctx->launches++; }
+  } else {
+    // batch / rows / columns: two block copies in the channels-last layout
+    B200_TRY(launch_copy_block(a->v, (*y)->v, 0, 0, 0, ctx->stream));
+    B200_TRY(launch_copy_block(b->v, (*y)->v, axis == 0 ? a->v.N : 0, axis == 2 ? a->v.H : 0, axis == 3 ? a->v.W : 0, ctx->stream));
+    ctx->launches += 2;
+  }
   return 0;
 }
 

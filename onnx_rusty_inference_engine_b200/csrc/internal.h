@@ -83,6 +83,7 @@ int launch_rows_to_nchw(TView src, float* dst_nchw, cudaStream_t st);
 int launch_nchw_to_s2d(const float* src_nchw, int N, int C, int H, int W, float* dst, cudaStream_t st, int* nonfinite = nullptr);
 int launch_nonfinite_scan(const float* p, size_t n, int* flag, cudaStream_t st);
 int launch_copy_rows(TView src, TView dst, cudaStream_t st);          // same N,C,H,W; pitches may differ
+int launch_copy_block(TView src, TView dst, int n0, int h0, int w0, cudaStream_t st);   // src into dst at pixel offset (n0, h0, w0)
 int launch_transpose2d(const float* src, int R, int C, float* dst, cudaStream_t st);  // dst[c][r] = src[r][c]
 // bandwidth_ops.cu
 int launch_relu(TView x, TView y, cudaStream_t st);

@@ -84,6 +84,21 @@ __global__ void copy_rows_vec4_kernel(const float4* __restrict__ src, float4* __
   }
 }
 
+// dst[(n + n0, h + h0, w + w0), c] <- src[(n, h, w), c]: a block of a larger tensor (Concat along N / H / W)
+__global__ void copy_block_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W, long long pixels, int lds,
+                                  int Hd, int Wd, int ldd, int n0, int h0, int w0) {
+  const long long total = pixels * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int c = (int)(i - pix * C);
+    const int w = (int)(pix % W);
+    const long long t = pix / W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    dst[(((n + n0) * Hd + (h + h0)) * (long long)Wd + (w + w0)) * ldd + c] = __ldg(src + pix * lds + c);
+  }
+}
+
 __global__ void transpose2d_kernel(const float* __restrict__ src, int R, int C, float* __restrict__ dst) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -235,6 +250,15 @@ int launch_copy_rows(TView src, TView dst, cudaStream_t st) {
     copy_rows_kernel<<<grid_for(pixels * src.C, kThreads), kThreads, 0, st>>>(src.p, dst.p, src.C, pixels,
                                                                                src.ld, dst.ld);
   }
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_copy_block(TView src, TView dst, int n0, int h0, int w0, cudaStream_t st) {
+  const long long pixels = src.pixels();
+  if (pixels == 0 || src.C == 0) return 0;
+  if (src.C != dst.C || n0 + src.N > dst.N || h0 + src.H > dst.H || w0 + src.W > dst.W) B200_FAIL(B200_EINVAL, "copy_block: block does not fit");
+  copy_block_kernel<<<grid_for(pixels * src.C, kThreads), kThreads, 0, st>>>(src.p, dst.p, src.C, src.H, src.W, pixels, src.ld, dst.H, dst.W, dst.ld, n0, h0, w0);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -105,23 +105,27 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const Stem
           const float2 v = *reinterpret_cast<const float2*>(t0 + r * TILE_W + c);
           in[r][c] = v.x; in[r][c + 1] = v.y;
         }
-      float acc[4][8];
+      // 32 accumulators as 16 channel pairs: one packed FFMA2 (fma.rn.f32x2, two IEEE fp32 FMAs per lane) per pair --
+      // the stem is issue-bound (ncu: 6.2 K warp instructions per image, 66 % issue slots, FMA pipe 57 %), and this
+      // halves its FMA instructions; each component is bit-identical to fmaf
+      float2 acc[4][4];
 #pragma unroll
       for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[p][c] = 0.f;
+        for (int c = 0; c < 4; ++c) acc[p][c] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < 5; ++r)
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
           const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 5 + s][0]);
           const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 5 + s][4]);
-          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float xv = in[(p >> 1) + r][(p & 1) + s];
+            const float2 xx = make_float2(xv, xv);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(xv, wv[c], acc[p][c]);
+            for (int c = 0; c < 4; ++c) acc[p][c] = __ffma2_rn(xx, wv[c], acc[p][c]);
           }
         }
       // (conv + bias) + add, Relu, max over the 2 x 2 window (fold from -FLT_MAX like max_pool_op.rs:337)
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const Stem
       for (int c = 0; c < 8; ++c) {
         float m = -3.402823466e+38f;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) m = fmaxf(m, fmaxf((acc[p][c] + sb[c]) + sa[c], 0.f));
+        for (int p = 0; p < 4; ++p) m = fmaxf(m, fmaxf((((c & 1) ? acc[p][c >> 1].y : acc[p][c >> 1].x) + sb[c]) + sa[c], 0.f));
         o[c] = m;
       }
       float* dst = a.p1 + (size_t)(img0 + im) * IMG_FLOATS + ((ph + 2) * PADW + (pw + 2)) * C1;
@@ -254,8 +258,13 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
         const uint32_t ad = buf + rowoff[i] + joff;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0[i].x), "=f"(x0[i].y), "=f"(x0[i].z), "=f"(x0[i].w) : "r"(ad + t0));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x1[i].x), "=f"(x1[i].y), "=f"(x1[i].z), "=f"(x1[i].w) : "r"(ad + t1));
-        if (z0) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (z1) x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (kb == NKB - 1) {   // warp-uniform: only the last k-block holds taps past K
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (z0) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (z1) x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
       // advance to this set's next k-block; on leaving a group, hand its buffer back once the loads above have delivered
       int nkb_ = kb + NSETS, nj = j, ngl = gl;

@@ -982,24 +982,37 @@ int Planner::do_concat(size_t i) {
   if (n.input.size() != 2) B200_FAIL(B200_EUNSUPPORTED, "Concat %s: exactly two inputs (concatenate_op.rs:15-18)", n.name.c_str());
   B200_TRY(attr_check(n, {"axis"}, "CONCATENATE"));
   const int64_t axis = attr_i(n, "axis", 1);
-  if (axis != 1) B200_FAIL(B200_EUNSUPPORTED, "Concat %s: only axis=1 is implemented", n.name.c_str());
+  if (axis < 0 || axis > 3) B200_FAIL(B200_EINVAL, "Concat %s: axis %lld out of range (concatenate_op.rs:31)", n.name.c_str(), (long long)axis);
   Val* a = get(n.input[0]);
   Val* b = get(n.input[1]);
   if (!a || !b || a->rank != 4 || b->rank != 4 || a->is_init || b->is_init)
     B200_FAIL(B200_EINVAL, "Concat %s: inputs must be rank-4 activations (concatenate_op.rs:16,18)", n.name.c_str());
-  if (a->dims[0] != b->dims[0] || a->dims[2] != b->dims[2] || a->dims[3] != b->dims[3])
-    B200_FAIL(B200_EINVAL, "Concat %s: non-axis dims differ", n.name.c_str());
+  for (int d = 0; d < 4; ++d)
+    if (d != axis && a->dims[d] != b->dims[d]) B200_FAIL(B200_EINVAL, "Concat %s: non-axis dims differ", n.name.c_str());
   auto it = env.find(n.output[0]);
-  if (it != env.end() && it->second.planned && redirect.count(n.input[0])) {
+  if (axis == 1 && it != env.end() && it->second.planned && redirect.count(n.input[0])) {
     return 0;  // both producers already wrote into the result: zero-copy
   }
-  Val y; y.rank = 4; y.dims[0] = a->dims[0]; y.dims[1] = a->dims[1] + b->dims[1]; y.dims[2] = a->dims[2]; y.dims[3] = a->dims[3];
+  Val y; y.rank = 4;
+  for (int d = 0; d < 4; ++d) y.dims[d] = a->dims[d];
+  y.dims[axis] += b->dims[axis];
   B200_TRY(place(n.output[0], &y));
-  TView av = a->v, bv = b->v, ya = y.v, yb = y.v;
-  ya.C = av.C; yb.C = bv.C; if (!dry) yb.p += av.C;
   std::string nm = n.name.empty() ? n.output[0] : n.name;
-  add_step(nm + ":0", "concat_copy", 0, 8.0 * (double)av.numel(), [av, ya](cudaStream_t st) { return launch_copy_rows(av, ya, st); });
-  add_step(nm + ":1", "concat_copy", 0, 8.0 * (double)bv.numel(), [bv, yb](cudaStream_t st) { return launch_copy_rows(bv, yb, st); });
+  TView av = a->v, bv = b->v;
+  if (axis == 1) {
+    TView ya = y.v, yb = y.v;
+    ya.C = av.C; yb.C = bv.C; if (!dry) yb.p += av.C;
+    add_step(nm + ":0", "concat_copy", 0, 8.0 * (double)av.numel(), [av, ya](cudaStream_t st) { return launch_copy_rows(av, ya, st); });
+    add_step(nm + ":1", "concat_copy", 0, 8.0 * (double)bv.numel(), [bv, yb](cudaStream_t st) { return launch_copy_rows(bv, yb, st); });
+  } else {
+    // batch / rows / columns (never used by the two bundled models): block copies in the channels-last layout.  Along the
+    // batch axis the result no longer scales with the planned batch like the inputs do; it is still what
+    // ndarray::concatenate(Axis(0)) returns for the planned tensors.
+    TView yv = y.v;
+    const int n0 = axis == 0 ? av.N : 0, h0 = axis == 2 ? av.H : 0, w0 = axis == 3 ? av.W : 0;
+    add_step(nm + ":0", "concat_copy", 0, 8.0 * (double)av.numel(), [av, yv](cudaStream_t st) { return launch_copy_block(av, yv, 0, 0, 0, st); });
+    add_step(nm + ":1", "concat_copy", 0, 8.0 * (double)bv.numel(), [bv, yv, n0, h0, w0](cudaStream_t st) { return launch_copy_block(bv, yv, n0, h0, w0, st); });
+  }
   env[n.output[0]] = y;
   return 0;
 }
@@ -1127,7 +1140,10 @@ int Planner::run() {
         shp[n.output[0]] = shp[n.input[0]];
       } else if (n.op_type == "Concat" && n.input.size() == 2 && have(n.input[0]) && have(n.input[1])) {
         auto a = shp[n.input[0]], b = shp[n.input[1]];
-        shp[n.output[0]] = {a[0], a[1] + b[1], a[2], a[3]};
+        const int64_t ax = attr_i(n, "axis", 1);
+        if (ax < 0 || ax > 3) continue;
+        a[(size_t)ax] += b[(size_t)ax];
+        shp[n.output[0]] = a;
       }
     }
     // fix channel offsets; drop redirects whose shapes are unknown or whose offsets break 16-byte alignment

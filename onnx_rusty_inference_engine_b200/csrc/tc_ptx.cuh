@@ -140,18 +140,36 @@ __device__ __forceinline__ float split_lo(float x, float hi) { return x - hi; }
 // warp's part of an A stage in tensor memory: hi -> columns [0,32), lo -> [32,64) of the stage; t_stage = lane
 // 32*quarter, column of the warp's 16-column half.  Two 16-lane halves: rows i = 2j, 2j+1 (split per half, so only 16
 // temporaries are live).
+// B200_SPLIT_RAW_HI (experiment, default 0).  The tensor core reads only the top 10 mantissa bits of a kind::tf32 operand,
+// i.e. it TRUNCATES, so the raw fp32 value can serve as the hi operand (parity tests green with it) and only
+// lo = x - trunc(x) needs computing: one LOP3 per element for -trunc(x) and one packed FADD2 per two elements, 1.5
+// instead of 2 issue slots per element.  Measured in one A/B run (profiles/README.md, round 2): slower, not faster --
+// conv1 0.549 -> 0.557 ms, fire6 expand3x3 0.129 -> 0.133, step 83.4k -> 82.1k img/s, MNIST head likewise: the packed
+// FADD2 needs aligned register pairs and ptxas answers with moves and spills under the producers' 72-register cap.
+#ifndef B200_SPLIT_RAW_HI
+#define B200_SPLIT_RAW_HI 0
+#endif
+__device__ __forceinline__ float neg_trunc_tf32(float x) { return __uint_as_float((__float_as_uint(x) & 0xFFFFE000u) ^ 0x80000000u); }
 __device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[4]) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const float4 a = x[2 * j], b = x[2 * j + 1];
+    const uint32_t ta = t_stage + ((uint32_t)(j * 16) << 16);
+#if B200_SPLIT_RAW_HI
+    tmem_st_16x256b_x2(ta, a.x, a.y, b.x, b.y, a.z, a.w, b.z, b.w);
+    const float2 a01 = __fadd2_rn(make_float2(a.x, a.y), make_float2(neg_trunc_tf32(a.x), neg_trunc_tf32(a.y)));
+    const float2 a23 = __fadd2_rn(make_float2(a.z, a.w), make_float2(neg_trunc_tf32(a.z), neg_trunc_tf32(a.w)));
+    const float2 b01 = __fadd2_rn(make_float2(b.x, b.y), make_float2(neg_trunc_tf32(b.x), neg_trunc_tf32(b.y)));
+    const float2 b23 = __fadd2_rn(make_float2(b.z, b.w), make_float2(neg_trunc_tf32(b.z), neg_trunc_tf32(b.w)));
+    tmem_st_16x256b_x2(ta + 32u, a01.x, a01.y, b01.x, b01.y, a23.x, a23.y, b23.x, b23.y);
+#else
     float4 ah, bh, al, bl;
     ah.x = split_hi(a.x); ah.y = split_hi(a.y); ah.z = split_hi(a.z); ah.w = split_hi(a.w);
     bh.x = split_hi(b.x); bh.y = split_hi(b.y); bh.z = split_hi(b.z); bh.w = split_hi(b.w);
-    const uint32_t ta = t_stage + ((uint32_t)(j * 16) << 16);
     tmem_st_16x256b_x2(ta, ah.x, ah.y, bh.x, bh.y, ah.z, ah.w, bh.z, bh.w);
     al.x = split_lo(a.x, ah.x); al.y = split_lo(a.y, ah.y); al.z = split_lo(a.z, ah.z); al.w = split_lo(a.w, ah.w);
     bl.x = split_lo(b.x, bh.x); bl.y = split_lo(b.y, bh.y); bl.z = split_lo(b.z, bh.z); bl.w = split_lo(b.w, bh.w);
     tmem_st_16x256b_x2(ta + 32u, al.x, al.y, bl.x, bl.y, al.z, al.w, bl.z, bl.w);
+#endif
   }
 }
-

@@ -238,6 +238,24 @@ def test_reshape_concat_dropout(ctx):
     assert np.array_equal(L.dropout(ctx, ctx.tensor(a), 0.5).numpy(), a)                           # dropout_op.rs:66-71
 
 
+@pytest.mark.parametrize("axis", [0, 1, 2, 3])
+def test_concat_any_axis(ctx, axis):
+    """concatenate_op.rs:31 takes any axis (ndarray::concatenate(Axis(axis)); both bundled models use 1)."""
+    from onnx_rusty_inference_engine_b200 import _lib as L
+    rng = np.random.default_rng(40 + axis)
+    sa, sb = [2, 6, 5, 7], [2, 6, 5, 7]
+    sb[axis] = 3
+    a, b = rng.standard_normal(sa, dtype=np.float32), rng.standard_normal(sb, dtype=np.float32)
+    got = L.concat(ctx, ctx.tensor(a), ctx.tensor(b), axis=axis).numpy()
+    assert np.array_equal(got, np.concatenate([a, b], axis=axis))
+    with pytest.raises(L.B200Error):
+        L.concat(ctx, ctx.tensor(a), ctx.tensor(b), axis=4)
+    if axis != 3:
+        bad = list(sa); bad[3] = 2
+        with pytest.raises(L.B200Error, match="non-axis dims differ"):
+            L.concat(ctx, ctx.tensor(a), ctx.tensor(rng.standard_normal(bad, dtype=np.float32)), axis=axis)
+
+
 def test_gap_softmax(ctx):
     from onnx_rusty_inference_engine_b200 import _lib as L
     from oracle import ref_ops as R
