@@ -685,12 +685,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
 // Weight preparation: w [M][ldw] (K valid floats per row) -> out [2*Mpad][Kpad]: tf32 hi rows, then lo rows.
 // Position 16g + j of an output row holds k = 16g + perm(j), the order in which tcgen05.st.16x256b lays the
 // activations' 16-float groups out in tensor-memory columns (see tmem_st_16x256b_x2).
-__global__ void tc_split_weights_kernel(const float* __restrict__ w, int M, int K, int ldw, float* __restrict__ out, int Mpad, int Kpad) {
+__global__ void tc_split_weights_kernel(const float* __restrict__ w, int M, int K, int ldw, float* __restrict__ out, int Mpad, int Kpad, int natural_k) {
   const long long total = (long long)Mpad * Kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / Kpad), kp = (int)(i - (long long)m * Kpad);
     const int j = kp & 15;
-    const int k = (kp & ~15) + (j < 8 ? 4 * (j >> 1) + (j & 1) : 4 * ((j - 8) >> 1) + 2 + (j & 1));
+    const int k = natural_k ? kp : (kp & ~15) + (j < 8 ? 4 * (j >> 1) + (j & 1) : 4 * ((j - 8) >> 1) + 2 + (j & 1));
     float x = 0.f;
     if (m < M && k < K) x = w[(long long)m * ldw + k];
     const float hi = tf32_rna(x);
@@ -741,7 +741,7 @@ int tc_supported(const ConvArgs& a) {
   return 0;
 }
 
-int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::shared_ptr<TcWeights>* out) {
+int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::shared_ptr<TcWeights>* out, bool natural_k) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   std::shared_ptr<TcWeights> t(new TcWeights());
@@ -753,7 +753,7 @@ int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::s
   if (cudaMalloc((void**)&t->buf, bytes) != cudaSuccess) { cudaGetLastError(); B200_FAIL(B200_ENOMEM, "cudaMalloc(%zu) for split weights", bytes); }
   const long long total = (long long)t->Mpad * t->Kpad;
   int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  tc_split_weights_kernel<<<blocks, 256, 0, st>>>(w_dev, M, K, K, t->buf, t->Mpad, t->Kpad);
+  tc_split_weights_kernel<<<blocks, 256, 0, st>>>(w_dev, M, K, K, t->buf, t->Mpad, t->Kpad, natural_k ? 1 : 0);
   B200_CUDA(cudaGetLastError());
   cuuint64_t gdim[2] = {(cuuint64_t)t->Kpad, (cuuint64_t)(2 * t->Mpad)};
   cuuint64_t gstride[1] = {(cuuint64_t)t->Kpad * sizeof(float)};

@@ -99,11 +99,13 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 // conv_tc.cu -- tcgen05 3xTF32 implicit GEMM.  Returns B200_EUNSUPPORTED when the shape is not eligible.
 struct TcWeights;  // pre-split (hi, lo) weight tiles + TMA descriptor, built once per weight tensor
 int tc_supported(const ConvArgs& a);
-int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::shared_ptr<TcWeights>* out);
+// natural_k: keep K in its natural order (producers that write whole rows with tcgen05.st.32x32b, mnist8_fused.cu) instead of
+// the 16-group permutation of tcgen05.st.16x256b (conv_tc.cu)
+int tc_prepare_weights(const float* w_dev, int M, int K, cudaStream_t st, std::shared_ptr<TcWeights>* out, bool natural_k = false);
 int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st);
 
 // mnist8_fused.cu -- the MNIST-8 graph in two launches (config 5: small-kernel regime)
-size_t mnist8_p1_floats(int N);   // floats of the zero-haloed stem output [N][18][18][8] (+ 64 B per image), N rounded up to 8
+size_t mnist8_p1_floats(int N);   // floats of the zero-haloed stem output [N][18][18][8] (+ 16 B per image), N rounded up to 8
 int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st, int* nonfinite = nullptr);
 int launch_mnist8_head(const float* p1, const TcWeights& w2, const float* bias2, const float* add2, const float* wm, const float* bm,
                        float* out, int N, cudaStream_t st);

@@ -10,19 +10,22 @@
 //                        (Convolution110, Plus112, ReLU114, Pooling160, Times212_reshape0, Times212, Plus214)
 //                        + reshape_op.rs:66-92, mul_op.rs:23, add_op.rs:84
 //
-// Between the two: the pooled stem output in a zero-haloed channels-last layout [N][18][18][8] (+ 64 bytes per image, see
-// IMG_STRIDE), 10.4 KB per image, written once and read once.  The regime is instruction-issue-bound, not HBM-bound
+// Between the two: the pooled stem output in a zero-haloed channels-last layout [N][18][18][8] (+ 16 bytes per image, see
+// IMG_FLOATS), 10.4 KB per image, written once and read once.  The regime is instruction-issue-bound, not HBM-bound
 // (3.2 KB in, 40 B out per image), so the design minimises issued instructions:
 //   * stem: one thread = one pooled pixel = a 6x6 input patch in registers, 2x2 conv pixels x 8 channels = 32
-//     accumulators, weights as broadcast 128-bit shared loads; 8 images per block iteration = 7 full passes of 224 threads.
+//     accumulators as packed pairs (fma.rn.f32x2), weights as broadcast 128-bit shared loads; 8 images per block
+//     iteration = 7 full passes of 224 threads.
 //   * head: conv2 as an implicit GEMM whose 128-row tiles are (8 images x 16 pool windows) at ONE of the 9 positions
 //     inside a 3x3 pool window.  MaxPool 3x3/3 is then an element-wise max over the 9 tiles' accumulators in the epilogue
 //     threads' registers -- no cross-lane traffic, no pooled-out pixels computed (rows / columns 12, 13 of the 14x14 map
-//     never reach the output: max_pool_op.rs:215-246 floors) -- and the MatMul is 160 FMAs per thread plus a 4-lane
-//     shuffle reduction.  A operand: 16 producer warps in 4 sets read the group's 83 KB from shared memory (one bulk
-//     copy per 8 images), split hi / lo in registers and write tensor memory (tcgen05.st), exactly the K layout of
-//     conv_tc.cu, so the weight preparation (tc_prepare_weights) is shared.  MMAs: per k-step A_hi x [B_hi; B_lo]
-//     (N = 32) and A_lo x B_hi (N = 16): 25.5 + 17.7 clk measured (profiles/r2_mma_issue_rates.txt).
+//     never reach the output: max_pool_op.rs:215-246 floors) -- and the MatMul is 160 FMAs per thread plus a shuffle /
+//     shared-memory reduction.  Tiles at neighbouring window positions read the same pooled-stem pixels under
+//     different taps, so the A operand is produced ONCE per input offset (7 x 7 blocks of 8 channels per group, not
+//     9 tiles x 25 taps): 8 producer warps read the group's 83 KB from shared memory (one bulk copy per 8 images), split
+//     hi / lo in registers and write their own tensor-memory rows (tcgen05.st.32x32b: natural K order, weights prepared
+//     with natural_k).  MMAs: per tap A_hi x [B_hi; B_lo] (N = 32) and A_lo x B_hi (N = 16): 25.5 + 17.7 clk measured
+//     (profiles/r2_mma_issue_rates.txt); the kernel is bound by that issue stream.
 // Numerics: 3xTF32 with {main | correction} accumulators like conv_tc.cu; bias / Add, Relu and the max commute
 // (x -> fl(x + b) and Relu are monotone), so max-then-add equals the reference's add-then-max bit for bit.
 #include <cstring>
@@ -40,9 +43,10 @@ constexpr int IN_HW = 28;                 // input 1 x 28 x 28
 constexpr int C1 = 8;                     // stem channels
 constexpr int P1_HW = 14;                 // pooled stem map
 constexpr int PADW = 18;                  // 14 + 2 * 2 halo
-constexpr int IMG_FLOATS = PADW * PADW * C1 + 16;   // 2,608 floats = 10,432 B: the 64 extra bytes make images 2k and 2k+1
-                                                     // differ by 64 B mod 128, so the two rows a quarter-warp reads in one
-                                                     // shared-memory phase (images 2k, 2k+1, same pixel) never share a bank
+constexpr int IMG_FLOATS = PADW * PADW * C1 + 4;    // 2,596 floats = 10,384 B = 16 B mod 128: the eight rows a quarter-warp of
+                                                     // the head's producers reads in one shared-memory phase are the eight
+                                                     // images of a group at the SAME pixel, so they fall in eight different
+                                                     // 16-byte bank groups
 constexpr int G = 8;                      // images per group = one 128-row tile per pool-window position
 constexpr int C2 = 16;                    // head conv channels
 constexpr int K2 = 200;                   // 5 * 5 * 8
@@ -63,32 +67,46 @@ struct StemArgs {
   int* nonfinite;        // set to 1 when the input holds an Inf / NaN (or null)
 };
 
-__global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const StemArgs a) {
-  __shared__ __align__(16) float tile[G][TILE_W * TILE_W];   // zero-haloed input images
-  __shared__ __align__(16) float ws[25][8];                   // weights, tap-major: two broadcast LDS.128 per tap
-  __shared__ float sb[8], sa[8];
+constexpr int STEM_TILE_FLOATS = G * TILE_W * TILE_W;                       // 8 zero-haloed 32 x 32 tiles
+constexpr int STEM_SMEM = (2 * STEM_TILE_FLOATS + 25 * 8 + 16) * 4;         // two tile buffers + weights + bias / add
+
+__global__ void __launch_bounds__(STEM_THREADS, 3) mnist8_stem_kernel(const StemArgs a) {
+  extern __shared__ __align__(16) float stem_smem[];
+  float* const tiles = stem_smem;                                            // [2][G][32 * 32]
+  float (*ws)[8] = reinterpret_cast<float (*)[8]>(stem_smem + 2 * STEM_TILE_FLOATS);   // weights, tap-major: two broadcast LDS.128 per tap
+  float* const sb = stem_smem + 2 * STEM_TILE_FLOATS + 200;
+  float* const sa = sb + 8;
   const int tid = threadIdx.x;
-  for (int i = tid; i < G * TILE_W * TILE_W; i += STEM_THREADS) (&tile[0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * STEM_TILE_FLOATS; i += STEM_THREADS) tiles[i] = 0.f;      // halos stay zero: only interiors are rewritten
   for (int i = tid; i < 200; i += STEM_THREADS) ws[i >> 3][i & 7] = __ldg(a.w + (i & 7) * 25 + (i >> 3));
   if (tid < 8) { sb[tid] = a.bias ? __ldg(a.bias + tid) : 0.f; sa[tid] = a.add ? __ldg(a.add + tid) : 0.f; }
+  __syncthreads();
   const int groups = (a.N + G - 1) / G;
-  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
-    __syncthreads();   // the previous group's compute has finished reading the tiles (and the first zero fill is visible)
-    // ---- stage 8 images: coalesced 128-bit reads (a 28-float row is 7 float4), interior of the zero-haloed tiles
+  // Stage 8 images into a tile buffer with cp.async (8-byte pieces: the interior of a haloed row starts at column 2):
+  // the copy of group i+1 is in flight while group i is computed (the ncu capture of the single-buffered version had
+  // 31 % of its stall samples in the load / barrier phase).
+  auto stage = [&](int g, int buf) {
     const int img0 = g * G;
     const int nimg = min(G, a.N - img0);
-    const float4* src = reinterpret_cast<const float4*>(a.x + (size_t)img0 * (IN_HW * IN_HW));
-    uint32_t mx = 0;
-    for (int i = tid; i < nimg * 196; i += STEM_THREADS) {
-      const float4 v = __ldg(src + i);
-      mx = max(max(mx, __float_as_uint(v.x) & 0x7fffffffu), max(__float_as_uint(v.y) & 0x7fffffffu, max(__float_as_uint(v.z) & 0x7fffffffu, __float_as_uint(v.w) & 0x7fffffffu)));
-      const int im = i / 196, q = i - im * 196, r = q / 7, c4 = q - r * 7;
-      float* d = &tile[im][(r + 2) * TILE_W + 2 + c4 * 4];   // 8-byte aligned
-      *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
-      *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
+    const float* src = a.x + (size_t)img0 * (IN_HW * IN_HW);
+    float* dstb = tiles + buf * STEM_TILE_FLOATS;
+    for (int i = tid; i < nimg * 392; i += STEM_THREADS) {     // 392 float2 per image, 14 per row
+      const int im = i / 392, q = i - im * 392, r = q / 14, c2 = q - r * 14;
+      const uint32_t d = smem_u32(dstb + im * (TILE_W * TILE_W) + (r + 2) * TILE_W + 2 + c2 * 2);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + 2 * i) : "memory");
     }
-    if (a.nonfinite && mx >= 0x7f800000u) *a.nonfinite = 1;
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int cur = 0;
+  if ((int)blockIdx.x < groups) stage(blockIdx.x, 0);
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, cur ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // buffer `cur` is complete for everyone, and everyone has finished computing from the other buffer
+    if (g + (int)gridDim.x < groups) stage(g + gridDim.x, cur ^ 1);
+    const int img0 = g * G;
+    const int nimg = min(G, a.N - img0);
+    const float (*tile)[TILE_W * TILE_W] = reinterpret_cast<const float (*)[TILE_W * TILE_W]>(tiles + cur * STEM_TILE_FLOATS);
+    uint32_t mx = 0;   // finite guard: every input pixel is the own position of exactly one conv pixel, checked there
     // ---- 7 passes: task = (image, pooled pixel)
 #pragma unroll 1
     for (int pass = 0; pass < 7; ++pass) {
@@ -105,6 +123,8 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const Stem
           const float2 v = *reinterpret_cast<const float2*>(t0 + r * TILE_W + c);
           in[r][c] = v.x; in[r][c + 1] = v.y;
         }
+      mx = max(max(mx, __float_as_uint(in[2][2]) & 0x7fffffffu), max(__float_as_uint(in[2][3]) & 0x7fffffffu,
+               max(__float_as_uint(in[3][2]) & 0x7fffffffu, __float_as_uint(in[3][3]) & 0x7fffffffu)));
       // 32 accumulators as 16 channel pairs: one packed FFMA2 (fma.rn.f32x2, two IEEE fp32 FMAs per lane) per pair --
       // the stem is issue-bound (ncu: 6.2 K warp instructions per image, 66 % issue slots, FMA pipe 57 %), and this
       // halves its FMA instructions; each component is bit-identical to fmaf
@@ -141,32 +161,43 @@ __global__ void __launch_bounds__(STEM_THREADS, 2) mnist8_stem_kernel(const Stem
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
     }
+    if (a.nonfinite && mx >= 0x7f800000u) *a.nonfinite = 1;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ head (tcgen05)
-constexpr int HEAD_WARPS = 24;
-constexpr int HEAD_THREADS = HEAD_WARPS * 32;   // 768
+// Tiles: row rho = image rho % 8, pool window rho / 8 (4 x 4 windows of 3 x 3 conv outputs); tile (jh, jw) holds the conv
+// output at position (jh, jw) of every window.  Tap (r, s) of tile (jh, jw) reads the pooled-stem pixel at offset
+// (jh + r, jw + s) from the window's origin: the SAME 128 x 8-channel block of the A operand serves up to nine
+// (tile, tap) pairs.  So the A operand is produced per INPUT-ROW offset r' = 0..6 as seven blocks s' = 0..6 (128 rows x 8
+// channels, hi and lo), 49 blocks per group instead of 9 tiles x 25 taps = 225: the producers' work drops 4.6x, and the
+// MMA warp walks r' and issues, for every tile with 0 <= r' - jh <= 4, the five taps of that kernel row.  All nine
+// accumulators of a group are live at once (9 x 32 columns), the A blocks of two input rows are double-buffered
+// (2 x 112 columns): 512 columns exactly.
+constexpr int HEAD_WARPS = 16;
+constexpr int HEAD_THREADS = HEAD_WARPS * 32;   // 512
 constexpr int EPI_WARPS = 4;                    // warps 0-3: TMEM lane quarter = warp
 constexpr int LOAD_WARP = 4, MMA_WARP = 5;      // warps 6, 7 idle (producers must start at a multiple of 4)
 constexpr int PROD_WARP0 = 8;
-constexpr int NSETS = 4, SET_WARPS = 4;         // 16 producer warps: set j fills k-blocks j, j + 4, ...
-constexpr int SA = 4;                           // A stages in tensor memory (one per set), 64 columns each: hi 32 | lo 32
-constexpr int NACC = 4;                         // accumulator stages, 32 columns each: main 16 | correction 16
-constexpr int A_COL0 = NACC * 32;
-constexpr uint32_t IMG_BYTES = IMG_FLOATS * 4;  // 10,432
-constexpr uint32_t GROUP_BYTES = G * IMG_BYTES; // 83,456
-constexpr uint32_t B_KB_BYTES = 2 * C2 * 128;   // one k-block of weights: [B_hi 16 rows | B_lo 16 rows] x 128 B
+constexpr int NSETS = 2, SET_WARPS = 4;         // 8 producer warps: set j fills the A buffer of input rows j, j + 2, ... (counted over groups)
+constexpr int NTILES = 9;                       // window positions = accumulators, 32 columns each: main 16 | correction 16
+constexpr int A_COL0 = NTILES * 32;             // 288
+constexpr int A_BUF_COLS = 112;                 // 7 blocks x 8 columns hi | 7 x 8 lo
+constexpr int NROWS = 7, NBLK = 7;              // input-row offsets r' and column offsets s' per group
+constexpr uint32_t IMG_BYTES = IMG_FLOATS * 4;  // 10,384
+constexpr uint32_t GROUP_BYTES = G * IMG_BYTES; // 83,072
+constexpr uint32_t B_KB_BYTES = 2 * C2 * 128;   // one k-block (4 taps) of weights: [B_hi 16 rows | B_lo 16 rows] x 128 B
 constexpr uint32_t SM_B = 0;                                    // 7 x 4 KB
-constexpr uint32_t SM_P1 = SM_B + NKB * B_KB_BYTES;             // 2 x 83,456 B
+constexpr uint32_t SM_P1 = SM_B + NKB * B_KB_BYTES;             // 2 x 83,072 B
 constexpr uint32_t SM_WM = SM_P1 + 2 * GROUP_BYTES;             // matmul weights [10][256] + bias [10] (+ pad)
 constexpr uint32_t SM_ADD = SM_WM + (NOUT * 256 + 16) * 4;      // conv bias [16] | add [16]
 constexpr uint32_t SM_PART = SM_ADD + 32 * 4;                   // [2][4 warps][8 img][10] partial logits
-constexpr uint32_t SM_TAP = SM_PART + 2 * 4 * 8 * NOUT * 4;     // tap offsets [7][4] (bytes) | tile offsets [9] (bytes)
-constexpr uint32_t SM_BARS = SM_TAP + (28 + 12) * 4;
-constexpr int NBARS = 1 + 2 + 2 + SA + SA + NACC + NACC;        // b_full | p1_full[2] | p1_empty[2] | full_a | empty_a | tmem_full | tmem_empty
+constexpr uint32_t SM_BARS = SM_PART + 2 * 4 * 8 * NOUT * 4;
+constexpr int NBARS = 1 + 2 + 2 + NSETS + NSETS + NTILES + NTILES;   // b_full | p1_full[2] | p1_empty[2] | full_a | empty_a | tmem_full | tmem_empty
 constexpr uint32_t SM_SLOT = SM_BARS + NBARS * 8;
 constexpr uint32_t HEAD_SMEM = SM_SLOT + 16 + 1024;             // + alignment slack
+static_assert(A_COL0 + 2 * A_BUF_COLS == 512, "tensor memory map");
+static_assert(IMG_BYTES % 128 == 16 && IMG_BYTES % 16 == 0, "image pitch: 16 bytes mod 128");
 
 struct HeadArgs {
   const float* p1;       // [N][IMG_FLOATS]
@@ -178,6 +209,13 @@ struct HeadArgs {
   int N;
 };
 
+// One row per lane: 8 consecutive 32-bit columns of the lane's own TMEM row (natural K order: column j = register j)
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(r0), "f"(r1), "f"(r2),
+               "f"(r3), "f"(r4), "f"(r5), "f"(r6), "f"(r7)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __grid_constant__ CUtensorMap tmapB, const HeadArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -187,9 +225,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
   auto p1_full = [&](int b) { return bars + 8u * (1 + b); };
   auto p1_empty = [&](int b) { return bars + 8u * (3 + b); };
   auto full_a = [&](int s) { return bars + 8u * (5 + s); };
-  auto empty_a = [&](int s) { return bars + 8u * (5 + SA + s); };
-  auto tmem_full = [&](int s) { return bars + 8u * (5 + 2 * SA + s); };
-  auto tmem_empty = [&](int s) { return bars + 8u * (5 + 2 * SA + NACC + s); };
+  auto empty_a = [&](int s) { return bars + 8u * (5 + NSETS + s); };
+  auto tmem_full = [&](int t) { return bars + 8u * (5 + 2 * NSETS + t); };
+  auto tmem_empty = [&](int t) { return bars + 8u * (5 + 2 * NSETS + NTILES + t); };
   const uint32_t tmem_slot = sbase + SM_SLOT;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int groups = (a.N + G - 1) / G;
@@ -199,19 +237,16 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
   // ---- per-CTA constants
   float* const wm_s = reinterpret_cast<float*>(gbase + SM_WM);
   float* const add_s = reinterpret_cast<float*>(gbase + SM_ADD);
-  uint32_t* const tap_s = reinterpret_cast<uint32_t*>(gbase + SM_TAP);
   for (int i = threadIdx.x; i < NOUT * 256; i += HEAD_THREADS) wm_s[i] = __ldg(a.wm + i);
   if (threadIdx.x < NOUT) wm_s[NOUT * 256 + threadIdx.x] = a.bm ? __ldg(a.bm + threadIdx.x) : 0.f;
   if (threadIdx.x < 16) { add_s[threadIdx.x] = a.bias2 ? __ldg(a.bias2 + threadIdx.x) : 0.f; add_s[16 + threadIdx.x] = a.add2 ? __ldg(a.add2 + threadIdx.x) : 0.f; }
-  if (threadIdx.x < 28) { const int t = threadIdx.x; tap_s[t] = t < 25 ? (uint32_t)(((t / 5) * PADW + (t % 5)) * C1 * 4) : 0u; }   // tap (r, s) -> byte offset
-  if (threadIdx.x >= 32 && threadIdx.x < 41) { const int j = threadIdx.x - 32; tap_s[28 + j] = (uint32_t)(((j / 3) * PADW + (j % 3)) * C1 * 4); }   // window position j
 
   if (warp == LOAD_WARP) {
     if (lane == 0) {
       mbar_init(b_full, 1);
       for (int b = 0; b < 2; ++b) { mbar_init(p1_full(b), 1); mbar_init(p1_empty(b), NSETS * SET_WARPS); }
-      for (int s = 0; s < SA; ++s) { mbar_init(full_a(s), SET_WARPS); mbar_init(empty_a(s), 1); }
-      for (int s = 0; s < NACC; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), EPI_WARPS); }
+      for (int s = 0; s < NSETS; ++s) { mbar_init(full_a(s), SET_WARPS); mbar_init(empty_a(s), 1); }
+      for (int t = 0; t < NTILES; ++t) { mbar_init(tmem_full(t), 1); mbar_init(tmem_empty(t), EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -225,67 +260,52 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   if (warp >= PROD_WARP0) {
-    // ================================================================ A producers: 4 sets x 4 warps
-    // Warp w owns TMEM lanes 32 * (w % 4) ..; a thread owns rows quarter*32 + 8i + lane/4 (i < 4) and, of each 128-byte
-    // k-block row, the 16-byte chunks (lane % 4) and 4 + (lane % 4).  Row rho of a tile = image rho % 8, pool window
-    // rho / 8; chunk c of k-block kb = tap 4 kb + c / 2, channels 4 (c % 2) .. + 3.
+    // ================================================================ A producers: 2 sets x 4 warps, a lane = a row
+    // Warp w owns TMEM lanes 32 * (w % 4) ..; lane l is row rho = 32 (w % 4) + l: image l % 8, window 4 (w % 4) + l / 8.
+    // Per input-row offset r' the thread reads the seven 32-byte pixels (r', 0..6) of its window from the group's buffer
+    // (a quarter-warp's eight lanes are the eight images at one pixel: image pitch = 16 bytes mod 128, conflict-free),
+    // splits them and writes its own TMEM row: hi block s' -> columns 8 s' .., lo block -> 56 + 8 s' ...
     const int pw_ = warp - PROD_WARP0;
     const int quarter = pw_ & 3, set = pw_ >> 2;
-    const int rsub = lane >> 2, cq = lane & 3;
-    uint32_t rowoff[4];   // byte offset of (image, window origin, channel half) inside a group buffer
+    const int img = lane & 7, win = quarter * 4 + (lane >> 3);
+    const uint32_t rowoff = (uint32_t)img * IMG_BYTES + (uint32_t)(((3 * (win >> 2)) * PADW + 3 * (win & 3)) * C1 * 4);
+    const uint32_t t_a = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(A_COL0 + set * A_BUF_COLS);
+    const int total_rows = my_groups * NROWS;
+    uint32_t ph = 0;                    // phase of this set's buffer (full_a / empty_a [set])
+    for (int idx = set; idx < total_rows; idx += NSETS) {
+      const int gl = idx / NROWS, rr = idx - gl * NROWS;
+      // the first row this warp touches in a group waits for the group's bulk copy
+      if (idx < NSETS || (idx - NSETS) / NROWS != gl) mbar_wait(p1_full(gl & 1), (uint32_t)(gl >> 1) & 1u);
+      const uint32_t src = sbase + SM_P1 + (uint32_t)(gl & 1) * GROUP_BYTES + rowoff + (uint32_t)(rr * PADW * C1 * 4);
+      float4 x[NBLK][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = quarter * 32 + i * 8 + rsub, img = row & 7, win = row >> 3;
-      rowoff[i] = (uint32_t)img * IMG_BYTES + (uint32_t)(((3 * (win >> 2)) * PADW + 3 * (win & 3)) * C1 * 4) + (uint32_t)((cq & 1) * 16);
-    }
-    const uint32_t t_a = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(A_COL0 + set * 64);   // this set's A stage
-    const int total_kb = my_groups * 9 * NKB;
-    uint32_t ph = 0;                    // phase of this set's stage (full_a / empty_a [set])
-    int kb = set, j = 0, gl = 0;        // position of k-block idx: k-block kb of tile j of the CTA's gl-th group
-    bool group_entered = false;
-    for (int idx = set; idx < total_kb; idx += NSETS) {
-      if (!group_entered) { mbar_wait(p1_full(gl & 1), (uint32_t)(gl >> 1) & 1u); group_entered = true; }
-      const uint32_t buf = sbase + SM_P1 + (uint32_t)(gl & 1) * GROUP_BYTES;
-      uint32_t joff, t0, t1;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(joff) : "r"(sbase + SM_TAP + 4u * (uint32_t)(28 + j)));
-      // chunk cq -> tap 4 kb + cq / 2 ; chunk 4 + cq -> tap 4 kb + 2 + cq / 2
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t0) : "r"(sbase + SM_TAP + 4u * (uint32_t)(kb * 4 + (cq >> 1))));
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(t1) : "r"(sbase + SM_TAP + 4u * (uint32_t)(kb * 4 + 2 + (cq >> 1))));
-      const bool z0 = kb * 4 + (cq >> 1) >= 25, z1 = kb * 4 + 2 + (cq >> 1) >= 25;   // past K: exact zeros (finite whatever the weights)
-      float4 x0[4], x1[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t ad = buf + rowoff[i] + joff;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0[i].x), "=f"(x0[i].y), "=f"(x0[i].z), "=f"(x0[i].w) : "r"(ad + t0));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x1[i].x), "=f"(x1[i].y), "=f"(x1[i].z), "=f"(x1[i].w) : "r"(ad + t1));
+      for (int sp = 0; sp < NBLK; ++sp) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[sp][0].x), "=f"(x[sp][0].y), "=f"(x[sp][0].z), "=f"(x[sp][0].w) : "r"(src + 32u * sp));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[sp][1].x), "=f"(x[sp][1].y), "=f"(x[sp][1].z), "=f"(x[sp][1].w) : "r"(src + 32u * sp + 16u));
       }
-      if (kb == NKB - 1) {   // warp-uniform: only the last k-block holds taps past K
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (z0) x0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (z1) x1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      // advance to this set's next k-block; on leaving a group, hand its buffer back once the loads above have delivered
-      int nkb_ = kb + NSETS, nj = j, ngl = gl;
-      if (nkb_ >= NKB) { nkb_ -= NKB; ++nj; if (nj == 9) { nj = 0; ++ngl; } }
-      const bool last_of_group = ngl != gl || idx + NSETS >= total_kb;
+      // leaving the group: hand its buffer back once the loads above have delivered (the arrive depends on them)
+      const bool last_of_group = idx + NSETS >= total_rows || (idx + NSETS) / NROWS != gl;
       if (last_of_group) {
-        const uint32_t dep = (__float_as_uint(x0[0].w) ^ __float_as_uint(x0[3].w) ^ __float_as_uint(x1[0].w) ^ __float_as_uint(x1[3].w)) & (uint32_t)(a.N >> 31);   // always 0, opaque
+        const uint32_t dep = (__float_as_uint(x[0][0].w) ^ __float_as_uint(x[3][1].w) ^ __float_as_uint(x[6][1].w)) & (uint32_t)(a.N >> 31);   // always 0, opaque
         __syncwarp();
         if (lane == 0) mbar_arrive(p1_empty(gl & 1) + dep);
-        group_entered = false;
       }
-      mbar_wait(empty_a(set), ph ^ 1u);   // the MMAs that read this stage have completed
+      mbar_wait(empty_a(set), ph ^ 1u);   // the MMAs that read this buffer have completed
       tc_fence_after();
-      split_store(t_a, x0);               // 64-byte half 0 of the k-block row: TMEM columns [0,16) hi / [32,48) lo
-      split_store(t_a + 16u, x1);         // half 1: columns [16,32) / [48,64)
+#pragma unroll
+      for (int sp = 0; sp < NBLK; ++sp) {
+        const float4 u = x[sp][0], v = x[sp][1];
+        const float h0 = split_hi(u.x), h1 = split_hi(u.y), h2 = split_hi(u.z), h3 = split_hi(u.w);
+        const float h4 = split_hi(v.x), h5 = split_hi(v.y), h6 = split_hi(v.z), h7 = split_hi(v.w);
+        tmem_st_32x32b_x8(t_a + 8u * sp, h0, h1, h2, h3, h4, h5, h6, h7);
+        tmem_st_32x32b_x8(t_a + 56u + 8u * sp, split_lo(u.x, h0), split_lo(u.y, h1), split_lo(u.z, h2), split_lo(u.w, h3),
+                          split_lo(v.x, h4), split_lo(v.y, h5), split_lo(v.z, h6), split_lo(v.w, h7));
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_a(set));
       ph ^= 1u;
-      kb = nkb_; j = nj; gl = ngl;
     }
   } else if (warp == LOAD_WARP) {
     // ================================================================ loader: weights once, then one bulk copy per group
@@ -313,59 +333,69 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
     const bool leader = elect_one();
     const uint32_t b_lo0 = (((sbase + SM_B) >> 4) & 0x3FFFu) | (1u << 16);
     mbar_wait(b_full, 0);
-    const int tiles = my_groups * 9;
-    int sa = 0;
+    int buf = 0;
     uint32_t pha = 0;
-    for (int t = 0; t < tiles; ++t) {
-      const int as = t & (NACC - 1);
-      mbar_wait(tmem_empty(as), (((uint32_t)t / NACC) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_main = tmem_base + (uint32_t)(as * 32), d_corr = d_main + (uint32_t)C2;
-#pragma unroll
-      for (int kb = 0; kb < NKB; ++kb) {
-        mbar_wait(full_a(sa), pha);
+    for (int gl = 0; gl < my_groups; ++gl) {
+      const uint32_t gph = (uint32_t)gl & 1u;
+#pragma unroll 1
+      for (int rr = 0; rr < NROWS; ++rr) {
+        mbar_wait(full_a(buf), pha);
         tc_fence_after();
-        if (leader) {
-          const uint32_t ah = tmem_base + (uint32_t)(A_COL0 + sa * 64), al = ah + 32u;
-          const uint32_t bl = b_lo0 + (uint32_t)kb * (B_KB_BYTES >> 4);
-          constexpr int KSTEPS_TAIL = 2;   // K = 200 = 6 k-blocks + 8 floats; K is permuted inside groups of 16 -> one whole group
+        const uint32_t a_hi = tmem_base + (uint32_t)(A_COL0 + buf * A_BUF_COLS), a_lo = a_hi + 56u;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (kb < NKB - 1 || kk < KSTEPS_TAIL) {
-              umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bl + 2 * kk), idesc32, (kb | kk) != 0 ? 1u : 0u);   // hi*hi -> main, hi*lo -> corr
-              umma_tf32_ts(d_corr, al + 8u * kk, sw128_desc(bl + 2 * kk), idesc16, 1u);                          // lo*hi -> corr
+        for (int jh = 0; jh < 3; ++jh) {
+          const int r = rr - jh;                 // kernel row of tile row jh that reads input row rr
+          if (r < 0 || r > 4) continue;          // warp-uniform
+          if (r == 0) {                          // first MMAs into these three accumulators in this group
+#pragma unroll
+            for (int jw = 0; jw < 3; ++jw) mbar_wait(tmem_empty(jh * 3 + jw), gph ^ 1u);
+            tc_fence_after();
+          }
+          if (leader) {
+#pragma unroll
+            for (int jw = 0; jw < 3; ++jw) {
+              const uint32_t d_main = tmem_base + (uint32_t)((jh * 3 + jw) * 32), d_corr = d_main + (uint32_t)C2;
+#pragma unroll
+              for (int s = 0; s < 5; ++s) {
+                const int tap = r * 5 + s;        // weights of tap (r, s): k-block tap / 4, 32-byte step tap % 4 inside its 128-byte rows
+                const uint32_t bl = b_lo0 + (uint32_t)(tap >> 2) * (B_KB_BYTES >> 4) + 2u * (uint32_t)(tap & 3);
+                umma_tf32_ts(d_main, a_hi + 8u * (uint32_t)(jw + s), sw128_desc(bl), idesc32, (r | s) != 0 ? 1u : 0u);   // hi*hi -> main, hi*lo -> corr
+                umma_tf32_ts(d_corr, a_lo + 8u * (uint32_t)(jw + s), sw128_desc(bl), idesc16, 1u);                         // lo*hi -> corr
+              }
             }
+          }
+          __syncwarp();
+          if (r == 4 && leader) {                 // last kernel row: these three tiles are complete
+#pragma unroll
+            for (int jw = 0; jw < 3; ++jw) umma_commit(tmem_full(jh * 3 + jw));
           }
         }
         __syncwarp();
-        if (leader) umma_commit(empty_a(sa));
-        if (++sa == SA) { sa = 0; pha ^= 1u; }
+        if (leader) umma_commit(empty_a(buf));
+        if (++buf == NSETS) { buf = 0; pha ^= 1u; }
       }
-      if (leader) umma_commit(tmem_full(as));
-      __syncwarp();
     }
   } else if (warp < EPI_WARPS) {
     // ================================================================ epilogue: max over the 9 tiles, Add, Relu, MatMul
     // Lane = row rho = 32 warp + lane of every tile: image rho % 8 = lane % 8, pool window rho / 8 = 4 warp + lane / 8.
-    const int img = lane & 7, win = warp * 4 + (lane >> 3);
+    const int win = warp * 4 + (lane >> 3);
     float* const part = reinterpret_cast<float*>(gbase + SM_PART);
-    int t = 0, gl = 0;
+    int gl = 0;
     for (int g = blockIdx.x; g < groups; g += gridDim.x, ++gl) {
       float m[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) m[c] = -3.402823466e+38f;   // fold start of max_pool_op.rs:337
-      for (int j = 0; j < 9; ++j, ++t) {
-        const int as = t & (NACC - 1);
-        mbar_wait(tmem_full(as), ((uint32_t)t / NACC) & 1u);
+      for (int t = 0; t < NTILES; ++t) {                        // tiles complete in this order (tile row jh after input row jh + 4)
+        mbar_wait(tmem_full(t), (uint32_t)gl & 1u);
         tc_fence_after();
         uint32_t acc[16], cor[16];
-        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * 32);
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * 32);
         tmem_ld16(ta, acc);
         tmem_ld16(ta + 16u, cor);
         tmem_ld_wait(acc, cor);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty(as));
+        if (lane == 0) mbar_arrive(tmem_empty(t));
 #pragma unroll
         for (int c = 0; c < 16; ++c) m[c] = fmaxf(m[c], __uint_as_float(acc[c]) + __uint_as_float(cor[c]));
       }
@@ -399,7 +429,6 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) mnist8_head_kernel(const __gr
         const float s = (pb[(0 * 8 + im) * NOUT + n] + pb[(1 * 8 + im) * NOUT + n]) + (pb[(2 * 8 + im) * NOUT + n] + pb[(3 * 8 + im) * NOUT + n]);
         if (g * G + im < a.N) a.out[(size_t)(g * G + im) * NOUT + n] = s + wm_s[NOUT * 256 + n];   // Plus214, add_op.rs:84
       }
-      (void)img;
     }
   }
 
@@ -424,7 +453,12 @@ int launch_mnist8_stem(const float* x, const float* w, const float* bias, const 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = groups < sms * 3 ? groups : sms * 3;
-  mnist8_stem_kernel<<<grid, STEM_THREADS, 0, st>>>(a);
+  static bool attr_set[64] = {false};
+  if (dev < 64 && !attr_set[dev]) {
+    B200_CUDA(cudaFuncSetAttribute(mnist8_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM));
+    attr_set[dev] = true;
+  }
+  mnist8_stem_kernel<<<grid, STEM_THREADS, STEM_SMEM, st>>>(a);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -956,10 +956,10 @@ int Planner::try_plan_mnist8(bool* done) {
   if (dry) { ++step_counter; return *done = true, 0; }
   std::shared_ptr<TcWeights> tcw;
   {
-    const std::string key = "tc:" + s2.w->name + ":8";
+    const std::string key = "tc:" + s2.w->name + ":8:natural_k";
     auto it = m->tc_weights.find(key);
     if (it == m->tc_weights.end()) {
-      B200_TRY(tc_prepare_weights(dw2, 16, 200, m->ctx->stream, &tcw));
+      B200_TRY(tc_prepare_weights(dw2, 16, 200, m->ctx->stream, &tcw, /*natural_k=*/true));
       m->tc_weights[key] = tcw;
     } else tcw = it->second;
   }
