@@ -121,7 +121,9 @@ struct TcParams {
 #include "tc_ptx.cuh"
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <bool HAS_ADD, bool EPI16>
+// NOPAD (gather layers whose taps all lie inside the image, e.g. conv1): a compile-time variant, so that the padded path's
+// masks and zero fill cost the no-padding producers neither registers nor instructions
+template <bool HAS_ADD, bool EPI16, bool NOPAD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -320,7 +322,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       auto issue = [&](float4 (&dst)[ROWS_PER_THREAD]) {
         uint32_t delta, r, sx, vm;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(delta), "=r"(r), "=r"(sx), "=r"(vm) : "r"(l_ent));
-        if (p.nopad) {
+        if (NOPAD) {
           // every tap is inside the image: four plain loads.  (The chunks past K in the last k-block have delta = 0:
           // they re-read tap (0,0) and meet zero weights, exact for finite data like the fused Fire module's zeros.)
 #pragma unroll
@@ -411,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       for (int i = 0; i < BM / 32; ++i) {
         int row = i * 32 + lane;
         const bool ok = row <= last_row;
-        const int rr = p.nopad ? min(row, last_row) : row;   // no masks: a row past the end re-reads the last pixel (never stored)
+        const int rr = NOPAD ? min(row, last_row) : row;   // no masks: a row past the end re-reads the last pixel (never stored)
         const int wsum = wo0 + rr;
         const int cw = p.magicWo ? (int)__umulhi((unsigned)wsum, p.magicWo) : wsum;   // wsum / Wo
         const int wo = wsum - cw * a.Wo;
@@ -862,10 +864,12 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   B200_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -884,12 +888,16 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
                      : CUDA_ERROR_NOT_SUPPORTED;
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
   }
+  const bool nopad = p.nopad && !p.a_tma;
   if (epi16) {
-    if (a.chan_add) conv_tc_kernel<true, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    if (a.chan_add) conv_tc_kernel<true, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  } else if (nopad) {
+    if (a.chan_add) conv_tc_kernel<true, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   } else {
-    if (a.chan_add) conv_tc_kernel<true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    if (a.chan_add) conv_tc_kernel<true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   }
   B200_CUDA(cudaGetLastError());
   return 0;
