@@ -108,6 +108,37 @@ def test_mnist_fused_path_vs_oracle_and_node_plan(ctx, batch):
     assert_close_mnist_noise(eng(xs), want, f"mnist node-by-node plan, batch {batch}")
 
 
+def test_mnist_config5_full_size(ctx):
+    """Config 5 at BASELINE.json's full size on one device: 65,536 N(0,10^2) images (seed 3) through the fused path.  Images
+    sampled from the run -- first / last group, both sides of the 148-CTA round-robin boundary, a ragged position -- against
+    the oracle; bitwise equality of sampled groups with small-batch runs of the same images (batch-position invariance at
+    full size); run-to-run determinism; and the pipelined host entry with two batch sizes interleaved."""
+    import torch
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    n = 65536
+    xs = synth.synthetic_batch(n, chw=(1, 28, 28), seed=3)
+    eng = Engine(MNIST_ONNX, ctx=ctx)
+    assert eng.model.launches_per_run(n) == 2
+    got = eng(xs)
+    assert got.shape == (n, 10) and np.isfinite(got).all()
+    idx = [0, 7, 8, 1183, 1184, 9471, 32768, 40001, 65528, 65535, 12345, 54321, 148 * 8 - 1, 148 * 8, 2 * 148 * 8 + 3, 60000]
+    want = rm.run_batch(ow.load_model(MNIST_ONNX), xs[idx], ["Input3", "Parameter193"], threads=8)
+    assert_close_mnist_noise(got[idx], want, "mnist batch 65536, sampled images vs oracle")
+    for g0 in (0, 1184, 40000, 65528):
+        assert np.array_equal(eng(xs[g0:g0 + 8]), got[g0:g0 + 8]), f"group at {g0}: batch-position invariance"
+    assert np.array_equal(eng(xs[65535:65536])[0], got[65535])
+    assert np.array_equal(eng(xs), got), "run-to-run determinism at full size"
+    a = torch.from_numpy(xs[:4096]).pin_memory(); b = torch.from_numpy(xs[4096:4096 + 1000]).pin_memory()
+    oa = torch.empty((4096, 10)).pin_memory(); ob = torch.empty((1000, 10)).pin_memory()
+    for _ in range(3):
+        eng.run_pinned_async(a, oa)
+        eng.run_pinned_async(b, ob)
+    eng.sync()
+    assert np.array_equal(oa.numpy(), got[:4096]) and np.array_equal(ob.numpy(), got[4096:5096])
+
+
 def test_squeezenet_synth_vs_oracle(ctx, synth_onnx):
     """Config 3 at test size: 6 seeded images through all 66 nodes vs the oracle, both executors."""
     from onnx_rusty_inference_engine_b200 import onnx_proto as P, synth
