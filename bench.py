@@ -120,7 +120,7 @@ def clock_regime(clocks) -> str:
     return "burst" if clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] else "sustained"
 
 
-def mnist_extra(torch, dist, local, world, rank, peaks, stream, steps=20, warmup=3):
+def mnist_extra(torch, dist, local, world, rank, peaks, stream, steps=50, warmup=10):
     """BASELINE.json configs[4]: MNIST-8, 65,536 synthetic images split over the run's GPUs (8,192 per GPU at 8), inputs
     resident, logits gathered on every rank inside the timed region.  Not the headline metric: an `extra` block."""
     from onnx_rusty_inference_engine_b200.inference_engine import Engine

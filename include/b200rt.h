@@ -173,8 +173,8 @@ int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float
  * kernel, 2 = force tcgen05 3xTF32), "fire_fusion" (0/1, default 1: expand1x1 + expand3x3 of a Fire module as one
  * launch when both fit one channel tile), "s2d" (0/1, default 1: a stride-2 stem convolution runs on a 2x2
  * space-to-depth copy of the graph input), "alt_order" (0/1, default 1: launches walk their tiles in alternating
- * directions so that each starts on what its predecessor left in the L2), "fused_cnn" (0/1, default 1: the MNIST-8 graph as two
- * fused launches when the graph matches), "finite_guard" (0/1, default 1: see below), "verbose" (0/1: print the reference's
+ * directions so that each starts on what its predecessor left in the L2), "fused_cnn" (0 / 1 / 2, default 2: the MNIST-8
+ * graph, when the graph matches, node by node / as two fused launches / as one launch), "finite_guard" (0/1, default 1: see below), "verbose" (0/1: print the reference's
  * per-node lines).
  * Finite guard: the tensor-core path splits every value into hi + lo (Inf - Inf = NaN) and some fusions add 0 * x terms, so
  * it reproduces the reference for FINITE inputs; the reference itself keeps an Inf / NaN local to the outputs that really

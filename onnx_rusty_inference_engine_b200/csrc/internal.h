@@ -106,9 +106,14 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st);
 
 // mnist8_fused.cu -- the MNIST-8 graph in two launches (config 5: small-kernel regime)
 size_t mnist8_p1_floats(int N);   // floats of the zero-haloed stem output [N][18][18][8] (+ 16 B per image), N rounded up to 8
-int launch_mnist8_stem(const float* x, const float* w, const float* bias, const float* add, float* p1, int N, cudaStream_t st, int* nonfinite = nullptr);
+struct Mnist8StemConsts { float w[25][8]; float bias[8]; float add[8]; };   // stem weights tap-major, Conv bias, folded Add (host copies: kernel parameters)
+int launch_mnist8_stem(const float* x, const Mnist8StemConsts& k, float* p1, int N, cudaStream_t st, int* nonfinite = nullptr);
 int launch_mnist8_head(const float* p1, const TcWeights& w2, const float* bias2, const float* add2, const float* wm, const float* bm,
                        float* out, int N, cudaStream_t st);
+
+// the same graph in ONE launch: stem warps (CUDA cores) one group ahead of the head (tcgen05) inside each persistent CTA
+int launch_mnist8_onepass(const float* x, const Mnist8StemConsts& k, const TcWeights& w2, const float* bias2, const float* add2, const float* wm,
+                          const float* bm, float* out, int N, cudaStream_t st, int* nonfinite = nullptr);
 
 // ---------------------------------------------------------------- geometry with the reference's quirks
 struct Geo { int Ho, Wo, pt, pb, pl, pr; };

@@ -95,7 +95,7 @@ def test_mnist_fused_path_vs_oracle_and_node_plan(ctx, batch):
     xs = synth.synthetic_batch(batch, chw=(1, 28, 28), seed=100 + batch)
     want = rm.run_batch(ow.load_model(MNIST_ONNX), xs, ["Input3", "Parameter193"], threads=8)
     eng = Engine(MNIST_ONNX, ctx=ctx)
-    assert eng.model.launches_per_run(batch) == 2, "the fused path should be two launches"
+    assert eng.model.launches_per_run(batch) == 1, "the fused path should be one launch"
     got = eng(xs)
     assert_close_mnist_noise(got, want, f"mnist fused, batch {batch}")
     unit = synth.synthetic_batch(batch, chw=(1, 28, 28), seed=200 + batch, std=1.0)   # unit-scale input: plain tolerance
@@ -103,6 +103,10 @@ def test_mnist_fused_path_vs_oracle_and_node_plan(ctx, batch):
     assert np.array_equal(eng(xs), got), "run-to-run determinism"
     k = batch // 2
     assert np.array_equal(eng(xs[k:k + 1])[0], got[k]), "batch-position invariance (bitwise)"
+    eng.model.set_option("fused_cnn", 1)                      # the two-launch form (pooled stem output through HBM)
+    assert eng.model.launches_per_run(batch) == 2
+    two = eng(xs)
+    assert np.array_equal(two, got), "one-launch and two-launch forms run the same arithmetic"
     eng.model.set_option("fused_cnn", 0)
     assert eng.model.launches_per_run(batch) == 5
     assert_close_mnist_noise(eng(xs), want, f"mnist node-by-node plan, batch {batch}")
@@ -120,7 +124,7 @@ def test_mnist_config5_full_size(ctx):
     n = 65536
     xs = synth.synthetic_batch(n, chw=(1, 28, 28), seed=3)
     eng = Engine(MNIST_ONNX, ctx=ctx)
-    assert eng.model.launches_per_run(n) == 2
+    assert eng.model.launches_per_run(n) == 1
     got = eng(xs)
     assert got.shape == (n, 10) and np.isfinite(got).all()
     idx = [0, 7, 8, 1183, 1184, 9471, 32768, 40001, 65528, 65535, 12345, 54321, 148 * 8 - 1, 148 * 8, 2 * 148 * 8 + 3, 60000]
