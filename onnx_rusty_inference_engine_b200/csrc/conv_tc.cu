@@ -114,6 +114,8 @@ struct TcParams {
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
   int nopad;       // every tap of every output pixel lies inside the image: no validity masks (gather mode)
+  int skip_cols;   // fused Fire expand: leading filters that are zero in k-blocks >= skip_kb (0 = none), a multiple of 16
+  int skip_kb;
   unsigned long long m64Wo, m64Ho, m64NT;   // ceil(2^64 / d), 0 when d == 1: exact n / d for n < 2^32 by one multiply-high
   uint32_t magicC, magicKW, magicWo, magicHo;  // ceil(2^32 / d), 0 when d == 1: exact n / d for n, d < 2^16
 };
@@ -179,7 +181,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   if (!p.a_tma) {
     for (int e = threadIdx.x; e < p.nkb * 8; e += NTHREADS) {
       const int k = e * 4;
-      const int tap = k / a.C, c = k - tap * a.C;
+      const int pos = k / a.C, c = k - pos * a.C;
+      const int tap = a.tap_perm ? (int)((a.tap_perm >> (4 * pos)) & 15ull) : pos;   // K position -> tap (planner's Fire fusion)
       const int r = tap / a.KW, sx = tap - r * a.KW;
       const bool ok = k < a.K;
       const int delta = ok ? (r * a.W + sx) * a.ldx + c : 0;
@@ -457,6 +460,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     // kept as 32-bit low words that advance by adds: +2 per k-step (32 bytes >> 4), +stage_bytes/16 per stage.
     // B200_TC_DEBUG bit 256 (timing experiment): issue every MMA with N = 16, whatever BN is
     const uint32_t idesc = instr_desc_tf32(TC_DBG(256) ? 16 : p.BN), idesc2 = instr_desc_tf32(TC_DBG(256) ? 16 : 2 * p.BN);
+    const uint32_t idesc_skip = instr_desc_tf32(p.BN - p.skip_cols);
     const bool leader = elect_one();
     const uint32_t lo_first = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);   // [0,14) address >> 4, [16,30) LBO = 1
     const uint32_t lo_step = (uint32_t)stage_bytes >> 4;
@@ -494,6 +498,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
                 umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + 2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
                 umma_tf32_ts(d_main, ah + 8u * kk, sw128_desc(bh + b_lo + 2 * kk), idesc, 1u);
                 umma_tf32_ts(d_main, al + 8u * kk, sw128_desc(bh + 2 * kk), idesc, 1u);
+              }
+            }
+          } else if (p.skip_cols > 0 && kb >= p.skip_kb) {
+            // Fused Fire expand: in these k-blocks the first skip_cols filters (the 1x1 branch, whose only tap sits in the
+            // first k-blocks) are exact zeros -- issue the other columns only: three N = BN - skip instructions per k-step
+            // instead of N = 2 BN + N = BN (BN = 128, skip = 64: 124 instead of 211 clk).  hi*hi -> main, hi*lo and lo*hi
+            // -> correction; B_hi / B_lo rows and accumulator columns offset by skip.
+            const uint32_t rs = (uint32_t)p.skip_cols * 8u;   // skip rows x 128 B >> 4
+            const uint32_t dm = d_main + (uint32_t)p.skip_cols, dc = d_corr + (uint32_t)p.skip_cols;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < ksteps) {
+                umma_tf32_ts(dm, ah + 8u * kk, sw128_desc(bh + rs + 2 * kk), idesc_skip, 1u);
+                umma_tf32_ts(dc, ah + 8u * kk, sw128_desc(bh + b_lo + rs + 2 * kk), idesc_skip, 1u);
+                umma_tf32_ts(dc, al + 8u * kk, sw128_desc(bh + rs + 2 * kk), idesc_skip, 1u);
               }
             }
           } else {
@@ -853,6 +872,10 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.m64NT = p.n_tiles_n == 1 ? 0ull : ~0ull / (unsigned long long)p.n_tiles_n + 1ull;
   p.m64Wo = a.Wo == 1 ? 0ull : ~0ull / (unsigned long long)a.Wo + 1ull;
   p.m64Ho = a.Ho == 1 ? 0ull : ~0ull / (unsigned long long)a.Ho + 1ull;
+  p.skip_cols = 0; p.skip_kb = 0;
+  if (a.skip_m > 0 && a.skip_m % 16 == 0 && a.skip_m + 16 <= p.BN && p.n_tiles_n == 1 && !p.merged && a.skip_kb >= 1 && a.skip_kb < p.nkb) {
+    p.skip_cols = a.skip_m; p.skip_kb = a.skip_kb;
+  }
   p.nopad = (a.pt == 0 && a.pl == 0 && (long long)(a.Ho - 1) * a.sh + a.KH <= a.H && (long long)(a.Wo - 1) * a.sw + a.KW <= a.W) ? 1 : 0;
   p.magicC = a.C == 1 ? 0u : (uint32_t)(((1ull << 32) + a.C - 1) / a.C);
   p.magicKW = a.KW == 1 ? 0u : (uint32_t)(((1ull << 32) + a.KW - 1) / a.KW);

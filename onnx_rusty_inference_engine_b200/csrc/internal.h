@@ -65,6 +65,11 @@ struct ConvArgs {
   // launch: a launch then starts on the part of its input that its predecessor wrote last and that is still in the
   // 126 MB L2.  Results do not depend on it (tiles are independent).
   int reverse;
+  // Fire expand fusion (planner): the K axis may list the taps in another order -- nibble i of tap_perm = the tap (r * KW + s)
+  // at K position i, 0 = natural order -- so that the centre tap comes first; the first skip_m filters (the 1x1 branch) are
+  // exact zeros outside the first skip_kb k-blocks, and the tcgen05 kernel does not issue their columns there.
+  unsigned long long tap_perm;
+  int skip_m, skip_kb;
 };
 
 struct PoolArgs {

@@ -522,18 +522,24 @@ int Planner::do_conv(size_t i) {
         if ((int64_t)w->init->f32.size() != (int64_t)M * C || (int64_t)w3->f32.size() != (int64_t)M3 * C * 9) break;
         // ---- committed: one 3x3 convolution with M + M3 filters
         const int Mt = M + M3;
-        std::string key = "convw:fire:" + w->init->name + "+" + w3->name + ":" + std::to_string(Ceff);
+        // K order of the fused filter bank: the centre tap first (tap_perm), so that the 1x1 branch's only non-zero
+        // weights sit in the first k-block(s) and the tcgen05 kernel can leave its columns out of all later k-blocks
+        static const int kPos2Tap[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+        unsigned long long tap_perm = 0;
+        for (int i = 0; i < 9; ++i) tap_perm |= (unsigned long long)kPos2Tap[i] << (4 * i);
+        std::string key = "convw:fire:ctr1st:" + w->init->name + "+" + w3->name + ":" + std::to_string(Ceff);
         float *dwf = nullptr, *dbf = nullptr;
         if (m->consts.count(key)) dwf = m->consts[key]->p;
         else {
           std::vector<float> h((size_t)Mt * 9 * Ceff, 0.f);
           for (int mm = 0; mm < M; ++mm)
-            for (int c = 0; c < C; ++c) h[(((size_t)mm * 3 + 1) * 3 + 1) * Ceff + c] = w->init->f32[(size_t)mm * C + c];
+            for (int c = 0; c < C; ++c) h[((size_t)mm * 9 + 0) * Ceff + c] = w->init->f32[(size_t)mm * C + c];   // K position 0 = centre tap
           for (int mm = 0; mm < M3; ++mm)
             for (int c = 0; c < C; ++c)
-              for (int r = 0; r < 3; ++r)
-                for (int sx = 0; sx < 3; ++sx)
-                  h[(((size_t)(M + mm) * 3 + r) * 3 + sx) * Ceff + c] = w3->f32[(((size_t)mm * C + c) * 3 + r) * 3 + sx];
+              for (int pos = 0; pos < 9; ++pos) {
+                const int r = kPos2Tap[pos] / 3, sx = kPos2Tap[pos] % 3;
+                h[((size_t)(M + mm) * 9 + pos) * Ceff + c] = w3->f32[(((size_t)mm * C + c) * 3 + r) * 3 + sx];
+              }
           B200_TRY(upload_const(m, key, h, &dwf));
         }
         if (bias || bias3) {
@@ -549,6 +555,9 @@ int Planner::do_conv(size_t i) {
         a.bias = dbf; a.chan_add = nullptr;
         a.Ho = g.Ho; a.Wo = g.Wo; a.sh = 1; a.sw = 1; a.pt = 1; a.pl = 1; a.relu = relu;
         a.reverse = next_reverse();
+        a.tap_perm = tap_perm;
+        a.skip_m = M;                        // the 1x1 filters ...
+        a.skip_kb = (Ceff + 31) / 32;        // ... are zero past the k-blocks that hold K position 0 (the centre tap)
         if (tc_supported(a) != 0) break;
         Val y1, y3;
         y1.rank = 4; memcpy(y1.dims, yd, sizeof(yd));
