@@ -587,6 +587,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         if (two_acc) tmem_ld16(t_main + (uint32_t)(p.BN + g_begin * 16), cor);
         tmem_ld_wait(acc, cor);
       }
+#pragma unroll 1   // unrolled, the short body makes ptxas spill the registers the pending tcgen05.ld write
       for (int g = g_begin; g < g_end; ++g) {
         if (!PIPE) {
           tmem_ld16(t_main + (uint32_t)(g * 16), acc);
@@ -600,32 +601,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           tmem_ld16(t_main + (uint32_t)((g + 1) * 16), acc);
           if (two_acc) tmem_ld16(t_main + (uint32_t)(p.BN + (g + 1) * 16), cor);
         }
-        const uint32_t boff = 4u * (uint32_t)(m0 + g * 16);
         const uint32_t crow = my_row + ((uint32_t)(g - g_begin) << 6);
-        // the shared-memory accesses are volatile asm (kept in program order), so batch them: four bias loads, the
-        // arithmetic, four slab stores -- one load latency per group instead of four
-        float4 b4[4], c4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b4[q].x), "=f"(b4[q].y), "=f"(b4[q].z), "=f"(b4[q].w) : "r"(sbias + boff + 16u * q));
-          if (HAS_ADD)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c4[q].x), "=f"(c4[q].y), "=f"(c4[q].z), "=f"(c4[q].w) : "r"(sadd + boff + 16u * q));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float bb[4] = {b4[q].x, b4[q].y, b4[q].z, b4[q].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = q * 4 + e;
-            float val = o[j] + bb[e];              // add_bias, convolution_op.rs:705 (0 when the node has no bias)
-            if (HAS_ADD) {                         // folded Add node, add_op.rs:75 (a second rounding, as upstream)
-              const float cc[4] = {c4[q].x, c4[q].y, c4[q].z, c4[q].w};
-              val = val + cc[e];
-            }
-            if (do_relu) val = fmaxf(val, 0.f);    // relu_op.rs:31-33
-            o[j] = val;
-          }
-        }
+        // The drain sits between two tiles' MMAs when there is one accumulator stage, and it is not the tensor-memory
+        // reads that make it long (tools/exp/ldtm_rates.cu: 8 warps drain 128 x 256 columns in ~400 clk) but its
+        // instructions, issued next to 16 busy producer warps: so only the sum goes to the slab here; bias, folded
+        // Add and Relu are applied by the store phase, after the accumulator has gone back to the MMA warp.
         // 16-byte chunk (g - g_begin) * 4 + q of the slab row, XOR-swizzled by the row
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -636,6 +616,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(as));
+      // bias (0 when the node has none: add_bias, convolution_op.rs:705), folded Add node (add_op.rs:75: a second
+      // rounding, as upstream), Relu (relu_op.rs:31-33) on the four channels m .. m+3 of a slab chunk
+      auto finish = [&](float4& v, const float4& bb, const float4& cc) {
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        if (HAS_ADD) { v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w; }
+        if (do_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      };
+      auto chan_consts = [&](int m, float4& bb, float4& cc) {   // m < Mpad: the shared-memory copies are zero padded
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(sbias + 4u * (uint32_t)m));
+        if (HAS_ADD) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cc.x), "=f"(cc.y), "=f"(cc.z), "=f"(cc.w) : "r"(sadd + 4u * (uint32_t)m));
+      };
       const int row0 = p0 + quarter * 32;                 // first pixel of this warp's 32 rows
       const int rows_valid = min(32, p.P - row0);          // <= 0 for a quarter past the end
       const int mbase = m0 + g_begin * 16;
@@ -652,6 +643,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           int rr = lane >> lw;
           const int m = mbase + c * 4;
           const int rows_ok = (m < a.M) ? rows_valid : 0;
+          float4 bb, cc = make_float4(0.f, 0.f, 0.f, 0.f);
+          chan_consts(m, bb, cc);   // the lane keeps its channels: one load for all rows
           float* dst = a.y + (long long)(row0 + rr) * a.ldy + m;
           const long long dstep = (long long)step * a.ldy;
           uint32_t src = slab + (uint32_t)(rr * p.slab_pitch) + ((uint32_t)c << 4);
@@ -662,8 +655,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
             const bool ok0 = rr < rows_ok, ok1 = rr + step < rows_ok;
             if (ok0) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(src ^ ((uint32_t)(rr & 7) << 4)));
             if (ok1) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"((src + sstep) ^ ((uint32_t)((rr + step) & 7) << 4)));
-            if (ok0) *reinterpret_cast<float4*>(dst) = v0;
-            if (ok1) *reinterpret_cast<float4*>(dst + dstep) = v1;
+            if (ok0) { finish(v0, bb, cc); *reinterpret_cast<float4*>(dst) = v0; }
+            if (ok1) { finish(v1, bb, cc); *reinterpret_cast<float4*>(dst + dstep) = v1; }
             rr += 2 * step; dst += 2 * dstep; src += 2 * sstep;
           }
           cdone += w;
@@ -679,6 +672,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
             float4 val;
             const uint32_t addr = slab + (uint32_t)(rr * p.slab_pitch) + (uint32_t)((c ^ (rr & 7)) << 4);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w) : "r"(addr));
+            float4 bb, cc = make_float4(0.f, 0.f, 0.f, 0.f);
+            chan_consts(m, bb, cc);
+            finish(val, bb, cc);
             float* dst = a.y + (long long)(row0 + rr) * a.ldy + m;
             if (p.vec_store && m + 4 <= a.M) {
               *reinterpret_cast<float4*>(dst) = val;

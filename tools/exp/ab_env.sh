@@ -1,12 +1,25 @@
 #!/bin/bash
-# A/B of an environment knob inside ONE gpurun call: bash tools/exp/ab_env.sh B200_TC_MERGED 0
-# (default build/knob first, then KNOB=VALUE), conv parity tests first.
-mkdir -p gpurun_out
-KNOB=${1:-B200_TC_MERGED}; VAL=${2:-0}
-timeout -s KILL 900 python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_models.py -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-echo "== default"; timeout -s KILL 300 python tools/tc_bench.py 2>&1 | tail -20
-echo "== $KNOB=$VAL"; env $KNOB=$VAL timeout -s KILL 300 python tools/tc_bench.py 2>&1 | tail -20
+# A/B of an experiment environment variable (default: B200_TC_NO_EMR=1 = the old single-barrier drain) on per-launch times
+# (bench.py's roofline.launches table) and tc_bench layers, interleaved in ONE gpurun call.   usage: ab_env.sh [VAR=VALUE]
+V=${1:-B200_TC_NO_EMR=1}
+O=gpurun_out/ab_env; mkdir -p $O; rm -f $O/*
+timeout 900 python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_models.py -m gpu -x -q 2>&1 | tail -4
+L="conv1 f2_fused f4_e3 f6_e3 f8_e3 f9_e3 f4_e1 f8_e1 conv10"
 for i in 1 2; do
-timeout -s KILL 600 python bench.py --no-cpu-baseline > gpurun_out/bench_on.json 2> gpurun_out/bench.err; echo "default rc=$?"; cut -c1-150 gpurun_out/bench_on.json; tail -2 gpurun_out/bench.err
-env $KNOB=$VAL timeout -s KILL 600 python bench.py --no-cpu-baseline > gpurun_out/bench_off.json 2> gpurun_out/bench.err; echo "$KNOB=$VAL rc=$?"; cut -c1-150 gpurun_out/bench_off.json
+  echo "== new" >> $O/layers.txt; timeout 300 python tools/tc_bench.py $L >> $O/layers.txt 2>&1
+  echo "== $V" >> $O/layers.txt; env $V timeout 300 python tools/tc_bench.py $L >> $O/layers.txt 2>&1
 done
+for i in 1 2 3; do
+  timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extra 2>/dev/null > $O/new_$i.json
+  env $V timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extra 2>/dev/null > $O/old_$i.json
+done
+cat $O/layers.txt
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/ab_env/*.json")):
+    try: d = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e: print(f, "no line", e); continue
+    L = d["roofline"].get("launches") or []
+    big = sorted(L, key=lambda x: -x["ms"])[:8]
+    print(f, round(d["value"]), round(d["ms_per_step"], 4), d["clocks"].get("sm_mhz"), d["roofline"]["regime"], [(str(x["name"])[:14], round(x["ms"], 4)) for x in big])
+PY
