@@ -110,6 +110,11 @@ struct TcParams {
   int vec_store;   // destination base and pitch are 16-byte aligned: 128-bit stores
   int a_tma;       // 1: A tiles arrive by TMA into a raw ring (pointwise layers); 0: register gather
   int R;           // raw ring slots (a_tma)
+  int raw_slot;    // bytes per raw ring slot: A_TILE_BYTES, or 2 * pool_rows + 1 window-row boxes in the pooled mode
+  int rowbox;      // pooled mode: bytes per window-row box (2*Wo+1 pixels x 128 B, rounded up to the 1 KB swizzle atom)
+  int tile_rows;   // output pixels per tile: BM, or pool_rows * Wo in the pooled mode
+  int pool_rows;   // pooled mode: a tile is pool_rows consecutive pooled rows of one image (MMA row = rho * Wo + j)
+  int pool_tpi;    // pooled mode: tiles per image = ceil(Ho / pool_rows)
   int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
@@ -125,7 +130,7 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------ the kernel
 // NOPAD (gather layers whose taps all lie inside the image, e.g. conv1): a compile-time variant, so that the padded path's
 // masks and zero fill cost the no-padding producers neither registers nor instructions
-template <bool HAS_ADD, bool EPI16, bool NOPAD>
+template <bool HAS_ADD, bool EPI16, bool NOPAD, bool POOL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -137,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   const int b_tile_bytes = p.BN * BK * 4;
   const int stage_bytes = 2 * b_tile_bytes;                                      // B_hi | B_lo
   const uint32_t raw_ring = smem_base + (uint32_t)p.S * stage_bytes;             // R x 16 KB raw fp32 A tiles (a_tma)
-  const uint32_t epi_slabs = raw_ring + (uint32_t)p.R * A_TILE_BYTES;            // 8 x 32 rows x slab_pitch
+  const uint32_t epi_slabs = raw_ring + (uint32_t)(p.R * p.raw_slot);            // 8 x 32 rows x slab_pitch
   const uint32_t sbias = epi_slabs + (uint32_t)(NUM_EPI_WARPS * 32 * p.slab_pitch);  // Mpad floats: bias, zero padded
   const uint32_t sadd = sbias + 4u * (uint32_t)p.Mpad;                           // Mpad floats: folded channel add
   const uint32_t bars = sadd + 4u * (uint32_t)p.Mpad;                            // 8-byte mbarriers
@@ -240,15 +245,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         const int row = quarter * 32 + i * 8 + rsub;
         off[i] = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
       }
+      if (POOL) {
+        // pooled mode: row rho * Wo + j of the tile is pixel j of the tile's pooled row rho; the slot holds the
+        // 2 * pool_rows + 1 input rows those windows touch (boxes of 2*Wo+1 pixels x 32 channels, first pixel = column
+        // -pool_pl), so the window of (rho, j) is pixels 2j .. 2j+2 of boxes 2 rho .. 2 rho + 2.  off[i] = pixel 2j of
+        // box 2 rho (a box is a multiple of 1 KB: the swizzle term is still pixel & 7).
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const int mrow = quarter * 32 + i * 8 + rsub;
+          const int rho = mrow / a.Wo, j = mrow - rho * a.Wo;
+          // rows past the tile's pixels are not computed (0xFFFFFFFF): with 54 of 128 rows in use two lane quarters idle
+          off[i] = rho < p.pool_rows ? (uint32_t)(2 * rho * p.rowbox) + (uint32_t)(2 * j) * 128u : 0xFFFFFFFFu;
+        }
+      }
       int r = kpar;
       uint32_t rph = 0;
       for (int idx = kpar; idx < items; idx += NSETS) {
         mbar_wait(raw_full(r), rph);
-        const uint32_t raw = raw_ring + (uint32_t)r * A_TILE_BYTES;
+        const uint32_t raw = raw_ring + (uint32_t)(r * p.raw_slot);
         float4 x[ROWS_PER_THREAD];
+        if (POOL) {
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i)
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            if (off[i] == 0xFFFFFFFFu) { x[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+            // pixel 2j is even: the swizzle term of pixels 2j, 2j+1, 2j+2 is (2j & 7), +1, (+2) & 7
+            const uint32_t px = off[i] >> 7;
+            const uint32_t a0 = raw + off[i] + (((uint32_t)chunk ^ (px & 7u)) << 4);
+            const uint32_t a1 = raw + off[i] + 128u + (((uint32_t)chunk ^ ((px + 1u) & 7u)) << 4);
+            const uint32_t a2 = raw + off[i] + 256u + (((uint32_t)chunk ^ ((px + 2u) & 7u)) << 4);
+            float4 m;
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+              const uint32_t ro = (uint32_t)(rr * p.rowbox);
+              float4 v0, v1, v2;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0.x), "=f"(v0.y), "=f"(v0.z), "=f"(v0.w) : "r"(a0 + ro) : "memory");
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(a1 + ro) : "memory");
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v2.x), "=f"(v2.y), "=f"(v2.z), "=f"(v2.w) : "r"(a2 + ro) : "memory");
+              // max_pool2d, max_pool_op.rs:157-360 (padding cells are zeros: the tensor map's out-of-bounds fill)
+              v0.x = fmaxf(fmaxf(v0.x, v1.x), v2.x); v0.y = fmaxf(fmaxf(v0.y, v1.y), v2.y);
+              v0.z = fmaxf(fmaxf(v0.z, v1.z), v2.z); v0.w = fmaxf(fmaxf(v0.w, v1.w), v2.w);
+              if (rr == 0) m = v0;
+              else { m.x = fmaxf(m.x, v0.x); m.y = fmaxf(m.y, v0.y); m.z = fmaxf(m.z, v0.z); m.w = fmaxf(m.w, v0.w); }
+            }
+            x[i] = m;   // depends on all nine loads: the release below waits for every one of them
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w) : "r"(raw + off[i]) : "memory");
+        }
         float4 hi[ROWS_PER_THREAD], lo[ROWS_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
@@ -442,12 +487,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       int r = 0;
       uint32_t rph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int p0 = tile_pt(t) * BM;
+        const int pt = tile_pt(t);
+        const int p0 = pt * BM;
+        // pooled mode: tile = pooled rows pool_rows * th .. of image n; their windows read 2 * pool_rows + 1 input rows
+        // from row 2 * pool_rows * th - pool_pt on
+        const int pn = POOL ? pt / p.pool_tpi : 0;
+        const int h0 = POOL ? 2 * p.pool_rows * (pt - pn * p.pool_tpi) - a.pool_pt : 0;
+        const int nbox = 2 * p.pool_rows + 1;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(raw_empty(r), rph ^ 1u);
-          mbar_expect_tx(raw_full(r), (uint32_t)A_TILE_BYTES);
-          // box = 32 channels x 128 pixel rows; rows past P and channels past C are zero-filled by the tensor map
-          tma_load_2d(raw_ring + (uint32_t)r * A_TILE_BYTES, &tmapA, raw_full(r), kb * BK, p0);
+          if (POOL) {
+            // boxes of 32 channels x (2 Wo + 1) pixels x one input row; rows / columns outside the image and channels
+            // past C are zero-filled by the tensor map -- the reference's MaxPool pads with zeros
+            const uint32_t box_tx = (uint32_t)(2 * a.Wo + 1) * 128u;
+            mbar_expect_tx(raw_full(r), (uint32_t)nbox * box_tx);
+            const uint32_t slot = raw_ring + (uint32_t)(r * p.raw_slot);
+            for (int rr = 0; rr < nbox; ++rr) tma_load_4d(slot + (uint32_t)(rr * p.rowbox), &tmapA, raw_full(r), kb * BK, -a.pool_pl, h0 + rr, pn);
+          } else {
+            mbar_expect_tx(raw_full(r), (uint32_t)A_TILE_BYTES);
+            // box = 32 channels x 128 pixel rows; rows past P and channels past C are zero-filled by the tensor map
+            tma_load_2d(raw_ring + (uint32_t)r * A_TILE_BYTES, &tmapA, raw_full(r), kb * BK, p0);
+          }
           if (++r == p.R) { r = 0; rph ^= 1u; }
         }
       }
@@ -568,7 +628,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       const int as = p.nacc == 2 ? (tc & 1) : 0;
       const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
       const int ptile = tile_pt(t);
-      const int p0 = ptile * BM;
+      // first output pixel of the tile and one past its last; pooled mode: pooled rows pool_rows * th .. of image pn
+      int p0, p_end;
+      if (POOL) {
+        const int pn = ptile / p.pool_tpi, th = ptile - pn * p.pool_tpi;
+        p0 = (pn * a.Ho + p.pool_rows * th) * a.Wo;
+        p_end = p0 + min(p.pool_rows, a.Ho - p.pool_rows * th) * a.Wo;
+      } else {
+        p0 = ptile * BM;
+        p_end = min(p.P, p0 + BM);
+      }
       const int m0 = tile_nt(t, ptile) * p.BN;
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
@@ -628,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         if (HAS_ADD) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cc.x), "=f"(cc.y), "=f"(cc.z), "=f"(cc.w) : "r"(sadd + 4u * (uint32_t)m));
       };
       const int row0 = p0 + quarter * 32;                 // first pixel of this warp's 32 rows
-      const int rows_valid = min(32, p.P - row0);          // <= 0 for a quarter past the end
+      const int rows_valid = min(32, p_end - row0);        // <= 0 for a quarter past the end (of the tile's pixels)
       const int mbase = m0 + g_begin * 16;
       if (TC_DBG(4)) {
       } else if (fast_store) {
@@ -753,6 +822,16 @@ int tc_supported(const ConvArgs& a) {
   if (a.Ho + BM >= 65536 || a.Wo + BM >= 65536) return B200_EUNSUPPORTED;                       // multiply-high division range
   if (a.K > 12288 || a.C >= 65536) return B200_EUNSUPPORTED;                                  // k decode table: 128 B per k-block in shared memory
   if ((long long)(a.KH + 1) * a.W * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;           // 32-bit tap offsets
+  if (a.pool) {
+    // fused MaxPool 3x3 / 2: pointwise stride-1 convolution on the pooled map, one pooled row (<= 128 pixels) per tile,
+    // one channel tile of <= 64 filters (the 8 + 16 role layout), window-row boxes of <= 256 pixels
+    if (a.KH != 1 || a.KW != 1 || a.sh != 1 || a.sw != 1 || a.pt != 0 || a.pl != 0) return B200_EUNSUPPORTED;
+    if (a.Wo < 1 || a.Wo > BM || a.Ho < 1 || 2 * a.Wo + 1 > 256 || a.M > 64 || a.pool_pt < 0 || a.pool_pl < 0 || a.pool_pt > 2 || a.pool_pl > 2) return B200_EUNSUPPORTED;
+    if ((long long)a.N * a.Ho >= (1ll << 31) - 1) return B200_EUNSUPPORTED;
+    // two raw slots (three window-row boxes each) + two weight stages + slabs, constants, barriers, tables must fit
+    const int rowbox = ((2 * a.Wo + 1) * 128 + 1023) & ~1023, bn = pick_bn(a.M);
+    if (2 * 3 * rowbox + 2 * (2 * bn * BK * 4) + 48 * 1024 > SMEM_MAX) return B200_EUNSUPPORTED;
+  }
   const long long P = (long long)a.N * a.Ho * a.Wo, in_pix = (long long)a.N * a.H * a.W;
   if (P >= (1ll << 31) - BM || (in_pix + (long long)a.W * 16) * a.ldx >= (1ll << 31)) return B200_EUNSUPPORTED;  // 32-bit element offsets in the producer
   return 0;
@@ -796,7 +875,28 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   p.n_tiles_n = w.Mpad / w.BN;
   p.reverse = a.reverse ? 1 : 0;
   p.zero = 0;
-  const long long tiles = ((P + BM - 1) / BM) * p.n_tiles_n;
+  if (a.pool && (tc_supported(a) != 0 || p.n_tiles_n != 1)) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: this shape cannot take a fused MaxPool (Wo=%d M=%d)", a.Wo, a.M);
+  // pooled mode: as many pooled rows per tile as fit the 128 MMA rows and two raw slots of 2 R + 1 window-row boxes in
+  // shared memory (R = 1 fits by tc_supported), evened out over the image (13 rows: 7 + 6, not 9 + 4)
+  p.pool_rows = 1; p.pool_tpi = 1;
+  p.rowbox = a.pool ? (((2 * a.Wo + 1) * 128 + 1023) & ~1023) : 0;
+  if (a.pool) {
+    // The launch is bound by the input stream, and what keeps HBM busy is bytes in flight: at least four raw slots
+    // (each k-block of a tile is one slot of 2 R + 1 boxes) matter more than full MMA tiles.  Measured (batch 256):
+    // pool1 -> fire2 squeeze R = 1 (four 42 KB slots) 0.206 ms, R = 2 (two 70 KB slots) 0.239; pool after fire4 ->
+    // fire5 squeeze R = 2 (five 35 KB slots) 0.151, R = 1 0.221, R = 4 (two 63 KB slots) 0.181; pool after fire8 ->
+    // fire9 squeeze R = 5 0.095, R = 7 0.116, R = 2 0.137 (MaxPool + Conv launches: 0.294 / 0.198 / 0.113)
+    const int room = SMEM_MAX - 2 * (2 * p.BN * BK * 4) - 48 * 1024;
+    int R = BM / a.Wo;
+    while (R > 1 && 4 * (2 * R + 1) * p.rowbox > room) --R;
+    static const int force_rows = [] { const char* e = getenv("B200_TC_POOL_ROWS"); return e ? atoi(e) : 0; }();   // experiments only
+    if (force_rows > 0 && force_rows * a.Wo <= BM && 2 * (2 * force_rows + 1) * p.rowbox <= room) R = force_rows;
+    if (R > a.Ho) R = a.Ho;
+    p.pool_tpi = (a.Ho + R - 1) / R;
+    p.pool_rows = (a.Ho + p.pool_tpi - 1) / p.pool_tpi;
+  }
+  p.tile_rows = a.pool ? p.pool_rows * a.Wo : BM;
+  const long long tiles = a.pool ? (long long)a.N * p.pool_tpi : ((P + BM - 1) / BM) * p.n_tiles_n;
   if (tiles >= (1ll << 31)) B200_FAIL(B200_EUNSUPPORTED, "too many tiles");
   p.total_tiles = (int)tiles;
   // tensor memory: accumulator stages {main | correction} x BN, then A stages of 64 columns
@@ -824,15 +924,16 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   // Pointwise layers (1x1, stride 1, no padding): im2col row p IS input pixel p, so the A operand is a plain 2-D
   // matrix [P][C] and TMA can stream it; these layers are HBM-bound and want many bytes in flight.
   static const int no_atma = [] { const char* e = getenv("B200_TC_NO_ATMA"); return e ? atoi(e) : 0; }();
-  p.a_tma = (!no_atma && a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.pt == 0 && a.pl == 0 && a.H == a.Ho && a.W == a.Wo) ? 1 : 0;
+  p.raw_slot = a.pool ? (2 * p.pool_rows + 1) * p.rowbox : A_TILE_BYTES;
+  p.a_tma = a.pool ? 1 : ((!no_atma && a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.pt == 0 && a.pl == 0 && a.H == a.Ho && a.W == a.Wo) ? 1 : 0);
   // Role layout: pointwise layers with wide tiles (BN > 64: one accumulator stage, so the drain is exposed, and for
   // the expand1x1 layers a 128 x BN tile per ~1000 clk of MMAs) run with 16 epilogue warps and 8 converter warps --
   // measured: conv10 0.210 -> 0.175 ms, expand1x1 3-6 % faster; squeeze layers (BN <= 64, HBM-bound) and BN = 64
   // expands are better off with 8 + 16, like everything that gathers.
   static const int force_epi16 = [] { const char* e = getenv("B200_TC_EPI16"); return e ? atoi(e) : -1; }();   // experiments only
-  bool epi16 = p.a_tma && p.BN > 64;
+  bool epi16 = p.a_tma && p.BN > 64 && !a.pool;
   if (force_epi16 == 0) epi16 = false;
-  if (force_epi16 == 1) epi16 = p.a_tma != 0;
+  if (force_epi16 == 1) epi16 = p.a_tma != 0 && !a.pool;
   const int n_epi = epi16 ? 16 : 8;
   const int groups_per_warp = ((p.BN >> 4) + n_epi / 4 - 1) / (n_epi / 4);
   p.slab_pitch = groups_per_warp <= 2 ? 128 : 256;
@@ -845,7 +946,8 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   if (S < 2) S = 2;
   if (p.a_tma) {
     if (S > 3) S = 3;
-    int R = (SMEM_MAX - fixed - S * stage_bytes) / A_TILE_BYTES;
+    if (a.pool && S > 2) S = 2;   // the raw slots are the large ones here; the whole weight matrix is a few stages anyway
+    int R = (SMEM_MAX - fixed - S * stage_bytes) / p.raw_slot;
     if (R > MAX_RAW) R = MAX_RAW;
     if (!epi16) R &= ~1;   // same for the raw ring
     if (R < 2) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for the raw A ring (BN=%d)", p.BN);
@@ -853,7 +955,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   }
   if ((size_t)S * stage_bytes + fixed > (size_t)SMEM_MAX) B200_FAIL(B200_EUNSUPPORTED, "tcgen05 conv: not enough shared memory for 2 weight stages (BN=%d)", p.BN);
   p.S = S;
-  const size_t smem = (size_t)S * stage_bytes + (size_t)p.R * A_TILE_BYTES + fixed;
+  const size_t smem = (size_t)S * stage_bytes + (size_t)p.R * p.raw_slot + fixed;
 
   p.vec_store = (a.ldy % 4 == 0 && (((uintptr_t)a.y) & 15) == 0) ? 1 : 0;
   {
@@ -883,12 +985,14 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   B200_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -896,7 +1000,19 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   CUtensorMap tmapA;
   memset(&tmapA, 0, sizeof(tmapA));
-  if (p.a_tma) {
+  if (a.pool) {
+    // the tensor BEFORE the pool as [N][H][W][C]; box = 32 channels x (2 Wo + 1) pixels of one row.  Coordinates outside
+    // the tensor (the pool's zero padding, channels past C in the last k-block) are filled with zeros.
+    EncodeTiledFn enc = get_encode_fn();
+    cuuint64_t gdim[4] = {(cuuint64_t)a.C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
+    cuuint64_t gstride[3] = {(cuuint64_t)a.ldx * sizeof(float), (cuuint64_t)a.W * a.ldx * sizeof(float), (cuuint64_t)a.H * a.W * a.ldx * sizeof(float)};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(2 * a.Wo + 1), 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc ? enc(&tmapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.x, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                     : CUDA_ERROR_NOT_SUPPORTED;
+    if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (pooled activation map) failed with %d (C=%d W=%d H=%d N=%d ldx=%d)", (int)r, a.C, a.W, a.H, a.N, a.ldx);
+  } else if (p.a_tma) {
     EncodeTiledFn enc = get_encode_fn();
     cuuint64_t gdim[2] = {(cuuint64_t)a.C, (cuuint64_t)P};
     cuuint64_t gstride[1] = {(cuuint64_t)a.ldx * sizeof(float)};
@@ -908,15 +1024,18 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
   }
   const bool nopad = p.nopad && !p.a_tma;
-  if (epi16) {
-    if (a.chan_add) conv_tc_kernel<true, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  if (a.pool) {
+    if (a.chan_add) conv_tc_kernel<true, false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+  } else if (epi16) {
+    if (a.chan_add) conv_tc_kernel<true, true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   } else if (nopad) {
-    if (a.chan_add) conv_tc_kernel<true, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    if (a.chan_add) conv_tc_kernel<true, false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   } else {
-    if (a.chan_add) conv_tc_kernel<true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    if (a.chan_add) conv_tc_kernel<true, false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
+    else conv_tc_kernel<false, false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
   }
   B200_CUDA(cudaGetLastError());
   return 0;

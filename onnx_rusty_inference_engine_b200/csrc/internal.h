@@ -70,6 +70,10 @@ struct ConvArgs {
   // exact zeros outside the first skip_kb k-blocks, and the tcgen05 kernel does not issue their columns there.
   unsigned long long tap_perm;
   int skip_m, skip_kb;
+  // MaxPool 3x3 / stride 2 (zero-fill padding pool_pt / pool_pl, the reference's) fused in front of a pointwise convolution
+  // (planner): x, H, W describe the tensor BEFORE the pool, Ho x Wo the pooled map the 1x1 convolution runs on.  tcgen05
+  // kernel only: the window rows arrive by TMA and the converter warps take the maximum on their way to tensor memory.
+  int pool, pool_pt, pool_pl;
 };
 
 struct PoolArgs {

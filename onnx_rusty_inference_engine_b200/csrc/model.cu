@@ -48,6 +48,11 @@ struct Val {  // one graph value for the planned batch
   // set when this value is a flatten of a channels-last activation whose NCHW order has been
   // folded into the consumer MatMul's weight: rows are in (h, w, c) order
   int perm_C = 0, perm_HW = 0;
+  // set when this value is a MaxPool 3x3 / 2 output that is never materialised: its only consumer, a pointwise
+  // convolution, pools on the fly (ConvArgs::pool).  pool_src is the pool's input; alloc is the input's allocation
+  bool pooled = false;
+  TView pool_src;
+  int pool_pt = 0, pool_pl = 0;
 };
 
 struct Step {
@@ -104,6 +109,7 @@ struct b200_model {
   int opt_cuda_graph = 1;
   int opt_conv_path = 0;
   int opt_fire_fusion = 1;
+  int opt_pool_fusion = 1;   // MaxPool 3x3 / 2 -> pointwise Conv as one tcgen05 launch that never writes the pooled tensor
   int opt_alt_order = 1;
   int opt_s2d = 1;           // stride-2 stem convolution on a space-to-depth copy of the graph input     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
   int opt_fused_cnn = 2;     // the MNIST-8 graph fused (mnist8_fused.cu) when the graph matches: 2 = one launch, 1 = two launches, 0 = node by node
@@ -201,6 +207,7 @@ struct Planner {
   std::map<std::string, int> n_consumers;
   std::map<std::string, std::pair<std::string, int>> redirect;  // value -> (concat output, channel offset)
   std::set<size_t> consumed;                                    // node indices folded into an earlier step
+  std::map<std::string, std::string> fused_pool_label;          // pooled value that is never materialised -> its MaxPool's name
   // ----- arena with liveness reuse.  The dry pass records every allocation with the launch that
   // first writes it (def) and the last launch that reads it (last); offsets then come from a first-fit interval
   // colouring: two allocations may share bytes iff their [def, last] launch ranges are disjoint (one in-order stream, so
@@ -485,7 +492,7 @@ int Planner::do_conv(size_t i) {
   // 3x3 convolution whose first M1 filters are the 1x1 weights at the centre tap and exact zeros elsewhere: the
   // tcgen05 kernel pays per MMA instruction, not per channel, below 128 channels, so the 1x1 branch rides along for
   // ~8 % of the 3x3 branch's time instead of a launch of its own.  Adding 0 * x terms is exact for finite x.
-  if (m->opt_fire_fusion && conv_path() != 1 && !chan_add && KH == 1 && KW == 1 && p.strides[0] == 1 && p.strides[1] == 1 &&
+  if (m->opt_fire_fusion && conv_path() != 1 && !x->pooled && !chan_add && KH == 1 && KW == 1 && p.strides[0] == 1 && p.strides[1] == 1 &&
       g.pt == 0 && g.pl == 0 && g.Ho == (int)x->dims[2] && g.Wo == (int)x->dims[3] && Ceff % 4 == 0) {
     auto r1 = redirect.find(out_name);
     if (r1 != redirect.end() && r1->second.second == 0) {
@@ -619,6 +626,11 @@ int Planner::do_conv(size_t i) {
     a.x = x->v.p; a.N = x->v.N; a.C = Ceff; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
     a.w = dw; a.M = M; a.KH = KH; a.KW = KW; a.K = KH * KW * Ceff; a.wc = Ceff; a.ldw = a.K;
     a.sh = (int)p.strides[0]; a.sw = (int)p.strides[1]; a.pt = g.pt; a.pl = g.pl;
+    if (x->pooled) {   // do_maxpool: the MaxPool in front of this pointwise convolution runs inside its launch
+      a.x = x->pool_src.p; a.H = x->pool_src.H; a.W = x->pool_src.W; a.ldx = x->pool_src.ld;
+      a.pool = 1; a.pool_pt = x->pool_pt; a.pool_pl = x->pool_pl;
+      label = fused_pool_label[n.input[0]] + " | " + label;
+    }
   }
   a.bias = db; a.chan_add = dadd;
   a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
@@ -626,7 +638,7 @@ int Planner::do_conv(size_t i) {
   a.reverse = next_reverse();
   const double P = (double)y.v.pixels();
   const double flops = 2.0 * P * M * C * KH * KW;
-  const double bytes = 4.0 * ((double)x->v.pixels() * C + P * M + (double)M * C * KH * KW);
+  const double bytes = 4.0 * ((double)(x->pooled ? x->pool_src.pixels() : x->v.pixels()) * C + P * M + (double)M * C * KH * KW);
   bool use_tc = false;
   std::shared_ptr<TcWeights> tcw;
   if (conv_path() != 1 && tc_supported(a) == 0) {
@@ -642,7 +654,9 @@ int Planner::do_conv(size_t i) {
   } else if (conv_path() == 2) {
     B200_FAIL(B200_EUNSUPPORTED, "Conv %s: conv_path=2 (tcgen05) requested but the shape is not eligible", label.c_str());
   }
-  if (use_tc) add_step(label, "conv_tc", flops, bytes, [a, tcw](cudaStream_t st) { return launch_conv_tc(a, *tcw, st); });
+  if (a.pool && !use_tc) B200_FAIL(B200_EUNSUPPORTED, "Conv %s: planned with a fused MaxPool but not eligible for the tcgen05 path", label.c_str());
+  // a pool-fused launch is bound by the pool's input traffic: it is listed with the bandwidth kernels, not with the conv family
+  if (use_tc) add_step(label, a.pool ? "maxpool+conv_tc" : "conv_tc", flops, bytes, [a, tcw](cudaStream_t st) { return launch_conv_tc(a, *tcw, st); });
   else add_step(label, "conv_simt", flops, bytes, [a](cudaStream_t st) { return launch_conv_simt(a, st); });
   env[out_name] = y;
   return 0;
@@ -659,6 +673,40 @@ int Planner::do_maxpool(size_t i) {
   Geo g;
   B200_TRY(ref_geometry(p.auto_pad, (int)x->dims[2], (int)x->dims[3], (int)p.kernel[0], (int)p.kernel[1], (int)p.strides[0], (int)p.strides[1], p.pads, &g));
   Val y; y.rank = 4; memcpy(y.dims, yd, sizeof(yd));
+  // ---- MaxPool 3x3 / 2 whose only consumer is a pointwise stride-1 convolution with <= 64 filters (SqueezeNet: pool1 ->
+  // fire2 squeeze, pool after fire4 -> fire5 squeeze): the convolution's launch pools on the fly -- the window rows arrive
+  // by TMA (out-of-bounds = the reference's zero padding) and the converter warps take the maximum on their way to tensor
+  // memory -- so the pooled tensor is neither written nor read back.  A tile is as many pooled rows of one image as fit
+  // the 128 MMA rows (54-pixel rows: 2, 27: 4, 13: 7 + 6).
+  size_t jc = 0;
+  if (m->opt_pool_fusion && conv_path() != 1 && p.kernel[0] == 3 && p.kernel[1] == 3 && p.strides[0] == 2 && p.strides[1] == 2 &&
+      g.Wo >= 4 && x->v.ld == x->v.C && !x->s2d && !x->pooled) {   // (dense rows: arena allocations are 256-byte aligned)
+    const WireNode* c = sole_consumer(n.output[0], &jc);
+    const WireTensor* cw = (c && c->op_type == "Conv" && c->input.size() >= 2 && c->input[0] == n.output[0]) ? m->wm.find_initializer(c->input[1]) : nullptr;
+    if (cw) {
+      auto wd = init_dims(m->wm, *cw);
+      b200_conv_params cp;
+      bool ok = wd.size() == 4 && wd[1] == x->v.C && wd[2] == 1 && wd[3] == 1 && wd[0] <= 64 && parse_conv_attrs(*c, &cp) == 0 &&
+                cp.strides[0] == 1 && cp.strides[1] == 1 && cp.pads[0] == 0 && cp.pads[1] == 0 && cp.pads[2] == 0 && cp.pads[3] == 0 &&
+                (cp.auto_pad == B200_PAD_NOTSET || cp.auto_pad == B200_PAD_VALID);
+      if (ok) {   // the same test launch_conv_tc applies (both planning passes must decide alike: no pointers involved)
+        ConvArgs t{};
+        t.N = x->v.N; t.C = x->v.C; t.H = x->v.H; t.W = x->v.W; t.ldx = x->v.ld; t.wc = t.C;
+        t.M = (int)wd[0]; t.KH = t.KW = 1; t.K = t.C; t.sh = t.sw = 1; t.Ho = g.Ho; t.Wo = g.Wo;
+        t.pool = 1; t.pool_pt = g.pt; t.pool_pl = g.pl;
+        ok = tc_supported(t) == 0;
+      }
+      if (ok) {
+        y.v.N = (int)yd[0]; y.v.C = (int)yd[1]; y.v.H = (int)yd[2]; y.v.W = (int)yd[3]; y.v.ld = y.v.C; y.v.p = nullptr;
+        y.pooled = true; y.pool_src = x->v; y.pool_pt = g.pt; y.pool_pl = g.pl;
+        y.alloc = x->alloc;   // reading the pooled value reads the pool's input: keeps it alive up to the convolution
+        y.planned = true;
+        env[n.output[0]] = y;
+        fused_pool_label[n.output[0]] = n.name.empty() ? n.output[0] : n.name;
+        return 0;
+      }
+    }
+  }
   B200_TRY(place(n.output[0], &y));
   PoolArgs a{};
   a.x = x->v.p; a.N = x->v.N; a.C = x->v.C; a.H = x->v.H; a.W = x->v.W; a.ldx = x->v.ld;
@@ -1424,6 +1472,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
     if (value < 0 || value > 2) B200_FAIL(B200_EINVAL, "conv_path must be 0, 1 or 2");
     if (m->opt_conv_path != (int)value) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_conv_path = (int)value;
+  } else if (k == "pool_fusion") {
+    if (m->opt_pool_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_pool_fusion = value ? 1 : 0;
   } else if (k == "fire_fusion") {
     if (m->opt_fire_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_fire_fusion = value ? 1 : 0;

@@ -144,6 +144,39 @@ def build_fire(cin: int, squeeze: int, expand: int, hw: int, seed: int = 0) -> b
     return P.encode("ModelProto", model)
 
 
+def build_pool_squeeze(cin: int, squeeze: int, hw: int, pads=(0, 0, 0, 0), seed: int = 0, tail: bool = False) -> bytes:
+    """MaxPool 3x3 / 2 followed by a pointwise squeeze convolution (test model for the pool fusion): data_0 [1, cin, hw, hw]
+    -> MaxPool(pads, auto_pad NOTSET: the reference honours pads only then, max_pool_op.rs:96) -> Conv 1x1 + Relu, which is
+    the graph output (tail=True: one more 1x1 Conv + Relu behind it, so the fused launch's output is an arena value)."""
+    rng = np.random.default_rng(seed)
+    nodes: List[Dict] = []
+    inits: List[Dict] = []
+    inputs: List[Dict] = [P.make_value_info("data_0", [1, cin, hw, hw])]
+    nodes.append(P.make_node("MaxPool", ["data_0"], ["pool_1"], name="pool", kernel_shape=[3, 3], strides=[2, 2],
+                             pads=list(pads), auto_pad="NOTSET"))
+    hp = (hw + pads[0] + pads[2] - 3) // 2 + 1
+
+    def conv(name: str, x: str, ci: int, co: int) -> str:
+        b = np.sqrt(6.0 / ci)
+        for nm, arr in ((f"{name}_w_0", rng.uniform(-b, b, size=(co, ci, 1, 1))), (f"{name}_b_0", rng.uniform(-0.1, 0.1, size=(co,)))):
+            inits.append(P.make_tensor(nm, arr.astype(np.float32), raw=True))
+            inputs.append(P.make_value_info(nm, arr.shape))
+        nodes.append(P.make_node("Conv", [x, f"{name}_w_0", f"{name}_b_0"], [f"{name}_1"], name=name,
+                                 kernel_shape=[1, 1], strides=[1, 1], pads=[0, 0, 0, 0]))
+        nodes.append(P.make_node("Relu", [f"{name}_1"], [f"{name}_2"], name=f"{name}_relu"))
+        return f"{name}_2"
+
+    y = conv("squeeze1x1", "pool_1", cin, squeeze)
+    co = squeeze
+    if tail:
+        y = conv("tail1x1", y, squeeze, 24)
+        co = 24
+    graph = {"node": nodes, "name": "pool-squeeze-synth", "initializer": inits, "input": inputs,
+             "output": [P.make_value_info(y, [1, co, hp, hp])]}
+    model = {"ir_version": 3, "producer_name": "b200-synth", "graph": graph, "opset_import": [{"domain": "", "version": 8}]}
+    return P.encode("ModelProto", model)
+
+
 def ensure_squeezenet(path: str, seed: int = 0) -> str:
     """Write the synthetic model to `path` if it is not there yet (deterministic for a given seed)."""
     if not os.path.exists(path):

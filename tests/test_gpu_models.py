@@ -213,6 +213,50 @@ def test_fire_module_alone(ctx, tmp_path, cin, squeeze, expand, hw, batch, fuses
     assert np.array_equal(eng(xs), fused), "tile walking direction must not change the bits"
 
 
+@pytest.mark.parametrize("cin,squeeze,hw,pads,batch,tail,neg", [
+    (32, 16, 55, (0, 0, 0, 0), 3, False, False),    # one k-block, 27 x 27 map: tiles of 4 pooled rows, the last of an image 3
+    (96, 16, 109, (0, 0, 0, 0), 2, False, False),   # pool1 -> fire2 squeeze: three k-blocks, tiles of 2 pooled rows of 54, 109-pixel window boxes
+    (64, 32, 54, (0, 0, 1, 1), 5, True, True),      # the pool after fire4: zero padding at the end, all-negative input (max with 0)
+    (48, 64, 57, (1, 1, 0, 0), 2, True, True),      # padding in front, channels end inside the second k-block, 64 filters
+    (256, 32, 54, (0, 0, 1, 1), 1, False, False),   # fire5 squeeze: eight k-blocks (raw ring wraps inside a tile)
+    (512, 64, 27, (0, 0, 0, 0), 3, False, False),   # the pool after fire8 -> fire9 squeeze: 13 x 13 map, tiles of 7 + 6 pooled rows, 16 k-blocks
+    (16, 8, 21, (0, 0, 0, 0), 5, True, True),       # 10 x 10 map in one tile, channels end inside the only k-block
+    (32, 16, 201, (0, 0, 0, 0), 1, False, False),   # 100 pooled pixels per row: every lane quarter of the tile in use, 78 KB raw slots
+    (32, 16, 261, (0, 0, 0, 0), 1, False, None),    # 130 pooled pixels per row: not eligible, stays MaxPool + Conv
+])
+def test_pool_fusion_matches_separate_launches(ctx, tmp_path, cin, squeeze, hw, pads, batch, tail, neg):
+    """MaxPool 3x3 / 2 -> pointwise Conv as ONE tcgen05 launch (window rows by TMA, maximum taken by the converter warps):
+    same bits as MaxPool kernel + convolution launch, one launch fewer, and the oracle's values
+    (max_pool_op.rs:157-360 zero-fill padding, convolution_op.rs:407-504)."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    from oracle import onnx_wire as ow, ref_model as rm
+    path = str(tmp_path / "pool_squeeze.onnx")
+    with open(path, "wb") as f:
+        f.write(synth.build_pool_squeeze(cin, squeeze, hw, pads=pads, seed=cin + hw, tail=tail))
+    xs = synth.synthetic_batch(batch, chw=(cin, hw, hw), seed=hw, std=1.0)
+    if neg:
+        xs = -np.abs(xs) - np.float32(0.25)
+    want = rm.run_batch(ow.load_model(path), xs, threads=2)
+    eng = Engine(path, ctx=ctx)
+    fused = eng(xs)
+    n_fused = eng.model.launches_per_run(batch)
+    kinds = [p["kind"] for p in eng.model.profile(batch, iters=1)]
+    assert_close(fused.reshape(want.shape), want, "pool fusion vs oracle")
+    if neg is None:
+        assert "maxpool" in kinds and "maxpool+conv_tc" not in kinds, kinds
+        return
+    assert "maxpool+conv_tc" in kinds and "maxpool" not in kinds, kinds
+    eng.model.set_option("pool_fusion", 0)
+    separate = eng(xs)
+    assert eng.model.launches_per_run(batch) == n_fused + 1
+    assert "maxpool" in [p["kind"] for p in eng.model.profile(batch, iters=1)]
+    assert np.array_equal(separate, fused), "the fused launch must give the bits of MaxPool + Conv"
+    eng.model.set_option("pool_fusion", 1)
+    eng.model.set_option("alt_order", 0)
+    assert np.array_equal(eng(xs), fused), "tile walking direction must not change the bits"
+
+
 def _assert_same_with_nonfinite(got, want, what):
     got = np.asarray(got); want = np.asarray(want)
     assert got.shape == want.shape

@@ -1,9 +1,18 @@
 #!/bin/bash
-# A/B of a model option inside ONE gpurun call: bash tools/exp/ab_option.sh pool_fusion
-mkdir -p gpurun_out
-OPT=${1:-pool_fusion}
-timeout -s KILL 600 python -m pytest tests/test_gpu_models.py -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-for i in 1 2; do
-timeout -s KILL 600 python bench.py --no-cpu-baseline --profile-out gpurun_out/pl_on.json > gpurun_out/bench_on.json 2> gpurun_out/bench.err; echo "$OPT=1 rc=$?"; cut -c1-150 gpurun_out/bench_on.json; tail -2 gpurun_out/bench.err
-timeout -s KILL 600 python bench.py --no-cpu-baseline --model-opt $OPT=0 --profile-out gpurun_out/pl_off.json > gpurun_out/bench_off.json 2> gpurun_out/bench.err; echo "$OPT=0 rc=$?"; cut -c1-150 gpurun_out/bench_off.json
+# A/B of a model option inside one process-independent pair of bench runs (bench.py --option k=v), interleaved, ONE gpurun call
+# usage: ab_option.sh pool_fusion     (runs the default and k=0)
+K=${1:-pool_fusion}
+O=gpurun_out/ab_option; mkdir -p $O; rm -f $O/*
+for i in 1 2 3; do
+  timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extra 2>/dev/null > $O/on_$i.json
+  timeout 300 python bench.py --steps 30 --no-cpu-baseline --no-extra --model-opt $K=0 2>/dev/null > $O/off_$i.json
 done
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob("gpurun_out/ab_option/*.json")):
+    try: d = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e: print(f, "no line", e); continue
+    L = d["roofline"].get("launches") or []
+    sel = [x for x in L if "pool" in x["name"] or "squeeze" in x["name"]][:8]
+    print(f, round(d["value"]), round(d["ms_per_step"], 4), d["clocks"].get("sm_mhz"), d["gpu_launches"], [(str(x["name"])[:26], x["kind"][:8], round(x["ms"], 4), x.get("gbs")) for x in sel])
+PY

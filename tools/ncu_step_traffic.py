@@ -3,7 +3,7 @@ usage: ncu_step_traffic.py launches.csv > profiles/<round>_step_dram_traffic.jso
 The CSV comes from
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c N --csv
 A step starts at the input transform (nchw_to_rows* or nchw_to_s2d*) and ends before the next one; the last COMPLETE step is kept."""
-import csv, json, sys
+import csv, json, re, sys
 
 rows = []
 with open(sys.argv[1]) as f:
@@ -15,7 +15,10 @@ order = []
 for r in rows:
     i = int(r["ID"])
     if i not in launches:
-        launches[i] = {"kernel": r["Kernel Name"].split("(")[0][-48:], "time": None, "dram_read": None, "dram_write": None}
+        full = r["Kernel Name"]
+        # conv_tc_kernel<HAS_ADD, EPI16, NOPAD, POOL>: the pool-fused instances are bandwidth launches, counted apart
+        pooled = re.search(r"conv_tc_kernel<\(bool\)\d, \(bool\)\d, \(bool\)\d, \(bool\)1>", full) is not None
+        launches[i] = {"kernel": full.split("(")[0][-48:] + ("POOL" if pooled else ""), "time": None, "dram_read": None, "dram_write": None}
         order.append(i)
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
@@ -38,7 +41,8 @@ for s in reversed(starts):
         break
 if step is None:
     sys.exit("no complete step found")
-conv = [l for l in step if "conv_tc_kernel" in l["kernel"]]
+conv = [l for l in step if "conv_tc_kernel" in l["kernel"] and not l["kernel"].endswith("POOL")]
+pooled = [l for l in step if l["kernel"].endswith("POOL")]
 out = {
     "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on "
            "bench.py --steps 2 --warmup 3; last complete step (tools/ncu_step_traffic.py)",
@@ -47,6 +51,9 @@ out = {
     "conv_tc_launches": len(conv),
     "conv_tc_dram_bytes_per_step": sum(l["dram_read"] + l["dram_write"] for l in conv),
     "conv_tc_time_per_step": sum(l["time"] for l in conv),
+    "pool_conv_tc_launches": len(pooled),
+    "pool_conv_tc_dram_bytes_per_step": sum(l["dram_read"] + l["dram_write"] for l in pooled),
+    "pool_conv_tc_time_per_step": sum(l["time"] for l in pooled),
     "step_time": sum(l["time"] for l in step),
 }
 json.dump(out, sys.stdout, indent=1)
