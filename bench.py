@@ -480,7 +480,9 @@ def run_own(args):
             "algorithmic_bytes": sum(p["bytes"] for p in conv), "algorithmic_flops": conv_flops,
             "per": f"step: the {len(conv)} conv launches (one kernel, conv_tc_kernel); duration = CUDA-event step time of the "
                    "timed region x the launches' share of the in-order per-launch event profile",
-            "kernel": f"conv (all {len(conv)} Conv launches of one step, 26 Conv nodes: " + ",".join(sorted({p['kind'] for p in conv})) + ")",
+            "kernel": f"conv (the {len(conv)} conv_tc launches of one step: " + ",".join(sorted({p['kind'] for p in conv})) + "; of the 26 Conv nodes, "
+                      f"{sum(1 for p in prof if p['kind'] == 'maxpool+conv_tc')} squeeze convolutions run inside the launch of the MaxPool in front of them -- "
+                      "HBM-bound launches, counted under hbm_ops with the pool's input bytes)",
             "peak_source": f"{peaks['src']}: bf16_tflops {peaks['bf16_tflops']} (burst) / bf16_tflops_sustained {peaks['bf16_tflops_sustained']}, / 2 (TF32) / 3 (3xTF32); "
                            f"regime '{regime}' chosen from the in-region clock samples",
             "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_share, "conv_ms_isolated_launches": conv_ms_isolated,

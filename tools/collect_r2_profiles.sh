@@ -21,6 +21,7 @@ cp $A/bench_reference.json profiles/r2_bench_reference_arm.json
 cp $A/per_launch_events.json profiles/r2_per_launch_events.json
 python tools/ncu_summary.py $A/prof_conv1.ncu-rep > profiles/r2_conv1_ncu_summary.txt 2>&1
 python tools/ncu_summary.py $A/prof_f2_fused.ncu-rep > profiles/r2_f2_fused_ncu_summary.txt 2>&1
+python tools/ncu_summary.py $A/prof_pool1_sq.ncu-rep > profiles/r2_pool1_squeeze_ncu_summary.txt 2>&1
 ncu -i $A/prof_mnist.ncu-rep --page raw --csv 2>/dev/null > gpurun_out/mn2.csv
 python - <<'PY'
 import csv

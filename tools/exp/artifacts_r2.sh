@@ -12,6 +12,9 @@ for L in conv1 f2_fused; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 1 -f -o $O/prof_$L python tools/tc_bench.py $L > $O/ncu_$L.log 2>&1
   echo "$L rc=$?"
 done
+# the pool-fused launch (pool1 | fire2 squeeze) is the second conv_tc_kernel launch of a run
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -f -o $O/prof_pool1_sq python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra > $O/ncu_pool1_sq.log 2>&1
+echo "pool1_sq rc=$?"
 timeout 100 python tools/mnist_bench.py 65536 3 > $O/plain_mnist.log 2>&1 &&
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:mnist8 -s 4 -c 2 -f -o $O/prof_mnist python tools/mnist_bench.py 65536 3 > $O/ncu_mnist.log 2>&1
 echo "mnist ncu rc=$?"
