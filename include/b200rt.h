@@ -172,7 +172,8 @@ int b200_model_run_device(b200_model *m, const float *d_in, int64_t batch, float
 /* Options: "cuda_graph" (0/1, default 1), "conv_path" (0 = auto, 1 = force CUDA-core fp32 cross-check
  * kernel, 2 = force tcgen05 3xTF32), "fire_fusion" (0/1, default 1: expand1x1 + expand3x3 of a Fire module as one
  * launch when both fit one channel tile), "pool_fusion" (0/1, default 1: a MaxPool 3x3 / 2 whose only consumer is a
- * pointwise convolution with <= 64 filters runs inside that convolution's launch; same bits), "s2d" (0/1, default 1: a stride-2 stem convolution runs on a 2x2
+ * pointwise convolution with <= 64 filters runs inside that convolution's launch; same bits), "pdl" (0/1, default 1:
+ * tcgen05 launches are programmatic dependent launches, their prologue runs under the predecessor's tail), "s2d" (0/1, default 1: a stride-2 stem convolution runs on a 2x2
  * space-to-depth copy of the graph input), "alt_order" (0/1, default 1: launches walk their tiles in alternating
  * directions so that each starts on what its predecessor left in the L2), "fused_cnn" (0 / 1 / 2, default 2: the MNIST-8
  * graph, when the graph matches, node by node / as two fused launches / as one launch), "finite_guard" (0/1, default 1: see below), "verbose" (0/1: print the reference's

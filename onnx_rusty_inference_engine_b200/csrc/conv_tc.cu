@@ -84,6 +84,14 @@ constexpr int MAX_A_STAGES = 4;
 #define B200_TC_DEBUG_MASKS 0
 #endif
 #define TC_DBG(bit) (B200_TC_DEBUG_MASKS && (p.debug & (bit)))
+// Role-mask build only, B200_TC_DEBUG bit 1024: CTA 0 stamps clock64() at the hand-over points of its first 96 tiles
+// (g_ts[role][tile][event]); launch_conv_tc prints them after the launch (tools/exp/tile_timeline.sh).
+#if B200_TC_DEBUG_MASKS
+__device__ unsigned long long g_ts[3][96][4];
+#define TC_TS(role, tile, ev) do { if ((p.debug & 1024) && blockIdx.x == 0 && (tile) < 96 && (threadIdx.x & 31) == 0) g_ts[role][tile][ev] = clock64(); } while (0)
+#else
+#define TC_TS(role, tile, ev) do { } while (0)
+#endif
 // Longest reduction that uses one merged accumulator (see launch_conv_tc).  0 = never: the merged accumulator triples the
 // truncating additions into the large accumulator, and on post-Relu (same-sign) inputs -- what the 3x3 expands really
 // see -- it measured 1.65x the tolerance at K = 288 and 0.84x at K = 144 (profiles/r2_accumulator_accuracy.txt;
@@ -134,6 +142,9 @@ template <bool HAS_ADD, bool EPI16, bool NOPAD, bool POOL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  // Programmatic dependent launch (ConvArgs::pdl): let the next launch on the stream take SMs as this grid's CTAs leave.
+  // A no-op when nothing was launched as a dependent.
+  asm volatile("griddepcontrol.launch_dependents;");
   using R_ = Roles<EPI16>;
   constexpr int NUM_EPI_WARPS = R_::NEPI, TMA_WARP = R_::TMA_WARP, MMA_WARP = R_::MMA_WARP, ATMA_WARP = R_::ATMA_WARP,
                 PROD_WARP0 = R_::PROD_WARP0, NSETS = R_::NSETS;
@@ -213,6 +224,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Everything above touched parameters and constants only (bias, decode tables, barriers, tensor memory).  From here on
+  // the roles read activations the previous launch wrote and overwrite buffers it may still be reading (the arena reuses
+  // dead buffers): wait until the grids this one depends on have completed and their writes are visible.  Returns at
+  // once when the launch was not a programmatic dependent.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);   // uniform for the compiler as well
@@ -533,8 +549,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tc) {
       const int as = p.nacc == 2 ? (tc & 1) : 0;
       const uint32_t aph = (p.nacc == 2 ? (uint32_t)(tc >> 1) : (uint32_t)tc) & 1u;
+      TC_TS(0, tc, 3);                       // arrived at the tile
       mbar_wait(tmem_empty(as), aph ^ 1u);   // epilogue has drained this accumulator stage
       tc_fence_after();
+      TC_TS(0, tc, 0);                       // accumulator stage free
       const uint32_t d_main = tmem_base + (uint32_t)(as * acc_cols);
       const uint32_t d_corr = p.merged ? d_main : d_main + (uint32_t)p.BN;
       const uint32_t b_lo = (uint32_t)b_tile_bytes >> 4;   // B_lo follows B_hi in the stage (descriptor units of 16 bytes)
@@ -542,6 +560,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         mbar_wait(full_a(sa), pha);  // A stage written to tensor memory by all 8 producer warps
         mbar_wait(full_b(s), ph);
         tc_fence_after();
+        if (kb == 0) TC_TS(0, tc, 1);   // first k-block's operands there
         if (leader && !TC_DBG(16)) {
           const uint32_t ah = tmem_base + (uint32_t)(a_col0 + sa * A_STAGE_COLS), al = ah + 32u;
           const uint32_t bh = lo;
@@ -598,6 +617,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       }
       if (leader) umma_commit(tmem_full(as));   // accumulator stage complete -> epilogue
       __syncwarp();
+      TC_TS(0, tc, 2);                           // last MMA issued
     }
    }
   } else {
@@ -639,8 +659,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         p_end = min(p.P, p0 + BM);
       }
       const int m0 = tile_nt(t, ptile) * p.BN;
+      if (warp == 0) TC_TS(1, tc, 3);   // arrived at the tile (previous store phase done)
       mbar_wait(tmem_full(as), aph);
       tc_fence_after();
+      if (warp == 0) TC_TS(1, tc, 0);   // accumulator complete
       const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * acc_cols);
       const bool two_acc = !p.merged;
       // software-pipelined drain (the extra registers come from setmaxnreg): the tcgen05.ld of group g+1 is in flight
@@ -685,6 +707,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(as));
+      if (warp == 0) TC_TS(1, tc, 1);   // drained
       // bias (0 when the node has none: add_bias, convolution_op.rs:705), folded Add node (add_op.rs:75: a second
       // rounding, as upstream), Relu (relu_op.rs:31-33) on the four channels m .. m+3 of a slab chunk
       auto finish = [&](float4& v, const float4& bb, const float4& cc) {
@@ -756,6 +779,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
           }
         }
       }
+      if (warp == 0) TC_TS(1, tc, 2);   // stored
       __syncwarp();   // the slab is rewritten by the next tile's drain
     }
   }
@@ -1024,20 +1048,39 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
     if (r != CUDA_SUCCESS) B200_FAIL(B200_ECUDA, "cuTensorMapEncodeTiled (activation map) failed with %d (C=%d P=%lld ldx=%d)", (int)r, a.C, P, a.ldx);
   }
   const bool nopad = p.nopad && !p.a_tma;
-  if (a.pool) {
-    if (a.chan_add) conv_tc_kernel<true, false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false, false, true><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-  } else if (epi16) {
-    if (a.chan_add) conv_tc_kernel<true, true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, true, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-  } else if (nopad) {
-    if (a.chan_add) conv_tc_kernel<true, false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false, true, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-  } else {
-    if (a.chan_add) conv_tc_kernel<true, false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-    else conv_tc_kernel<false, false, false, false><<<grid, NTHREADS, smem, st>>>(w.tmap, tmapA, p);
-  }
+  void (*kernel)(const CUtensorMap, const CUtensorMap, const TcParams);
+  if (a.pool) kernel = a.chan_add ? conv_tc_kernel<true, false, false, true> : conv_tc_kernel<false, false, false, true>;
+  else if (epi16) kernel = a.chan_add ? conv_tc_kernel<true, true, false, false> : conv_tc_kernel<false, true, false, false>;
+  else if (nopad) kernel = a.chan_add ? conv_tc_kernel<true, false, true, false> : conv_tc_kernel<false, false, true, false>;
+  else kernel = a.chan_add ? conv_tc_kernel<true, false, false, false> : conv_tc_kernel<false, false, false, false>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, w.tmap, tmapA, p));
   B200_CUDA(cudaGetLastError());
+#if B200_TC_DEBUG_MASKS
+  if (p.debug & 1024) {   // tile timeline of CTA 0 (clk relative to the first stamp)
+    B200_CUDA(cudaStreamSynchronize(st));
+    static unsigned long long h[3][96][4];
+    B200_CUDA(cudaMemcpyFromSymbol(h, g_ts, sizeof(h)));
+    const unsigned long long t0 = h[0][0][3];
+    const int nt = std::min(96, (p.total_tiles + grid - 1) / grid);
+    fprintf(stderr, "tile timeline BN=%d K=%d tiles/CTA=%d: tile | MMA arrive, acc free, operands, last issue | EPI arrive, acc full, drained, stored\n", p.BN, a.K, nt);
+    for (int t = 0; t < nt; ++t)
+      fprintf(stderr, "%3d | %8lld %8lld %8lld %8lld | %8lld %8lld %8lld %8lld\n", t, (long long)(h[0][t][3] - t0), (long long)(h[0][t][0] - t0), (long long)(h[0][t][1] - t0),
+              (long long)(h[0][t][2] - t0), (long long)(h[1][t][3] - t0), (long long)(h[1][t][0] - t0), (long long)(h[1][t][1] - t0), (long long)(h[1][t][2] - t0));
+    static unsigned long long zero[3][96][4];
+    B200_CUDA(cudaMemcpyToSymbol(g_ts, zero, sizeof(zero)));
+  }
+#endif
   return 0;
 }
 

@@ -74,6 +74,10 @@ struct ConvArgs {
   // (planner): x, H, W describe the tensor BEFORE the pool, Ho x Wo the pooled map the 1x1 convolution runs on.  tcgen05
   // kernel only: the window rows arrive by TMA and the converter warps take the maximum on their way to tensor memory.
   int pool, pool_pt, pool_pl;
+  // Programmatic dependent launch (planner, tcgen05 kernel): the launch may begin while its predecessor on the stream is
+  // still running -- its CTAs take SMs as the predecessor's CTAs leave and run their prologue (barriers, tensor-memory
+  // allocation, decode tables, first weight tiles); every access to activations comes after griddepcontrol.wait.
+  int pdl;
 };
 
 struct PoolArgs {

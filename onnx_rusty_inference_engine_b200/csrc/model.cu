@@ -109,6 +109,7 @@ struct b200_model {
   int opt_cuda_graph = 1;
   int opt_conv_path = 0;
   int opt_fire_fusion = 1;
+  int opt_pdl = 1;           // tcgen05 launches as programmatic dependent launches (prologue under the predecessor's tail)
   int opt_pool_fusion = 1;   // MaxPool 3x3 / 2 -> pointwise Conv as one tcgen05 launch that never writes the pooled tensor
   int opt_alt_order = 1;
   int opt_s2d = 1;           // stride-2 stem convolution on a space-to-depth copy of the graph input     // alternate the tile walking direction from launch to launch (L2 reuse)   // expand1x1 + expand3x3 of a Fire module as one conv when both fit one channel tile
@@ -315,6 +316,7 @@ struct Planner {
   // squeeze the opposite of the last expand.
   size_t step_counter = 0;
   int next_reverse() const { return m->opt_alt_order ? (int)(step_counter & 1) : 0; }
+  int use_pdl() const { return m->opt_pdl ? 1 : 0; }
   void add_step(const std::string& name, const char* kind, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
     ++step_counter;
     if (dry) return;
@@ -562,6 +564,7 @@ int Planner::do_conv(size_t i) {
         a.bias = dbf; a.chan_add = nullptr;
         a.Ho = g.Ho; a.Wo = g.Wo; a.sh = 1; a.sw = 1; a.pt = 1; a.pl = 1; a.relu = relu;
         a.reverse = next_reverse();
+        a.pdl = use_pdl();
         a.tap_perm = tap_perm;
         a.skip_m = M;                        // the 1x1 filters ...
         a.skip_kb = (Ceff + 31) / 32;        // ... are zero past the k-blocks that hold K position 0 (the centre tap)
@@ -636,6 +639,7 @@ int Planner::do_conv(size_t i) {
   a.y = y.v.p; a.Ho = g.Ho; a.Wo = g.Wo; a.ldy = y.v.ld;
   a.relu = relu;
   a.reverse = next_reverse();
+  a.pdl = use_pdl();
   const double P = (double)y.v.pixels();
   const double flops = 2.0 * P * M * C * KH * KW;
   const double bytes = 4.0 * ((double)(x->pooled ? x->pool_src.pixels() : x->v.pixels()) * C + P * M + (double)M * C * KH * KW);
@@ -871,6 +875,7 @@ int Planner::do_matmul(size_t i) {
   c.y = y.v.p; c.Ho = 1; c.Wo = 1; c.ldy = y.v.ld; c.sh = c.sw = 1; c.pt = c.pl = 0; c.relu = 0;
   const double R = (double)a->dims[0];
   c.reverse = next_reverse();
+  c.pdl = use_pdl();
   // mul_op.rs:23 on the convolution's tcgen05 path: rows are the "pixels" of a pointwise layer (TMA-fed A tiles), the
   // N columns one channel tile (MNIST: 10 -> BN = 16)
   if (conv_path() != 1 && tc_supported(c) == 0) {
@@ -1472,6 +1477,9 @@ int b200_model_set_option(b200_model* m, const char* key, int64_t value) {
     if (value < 0 || value > 2) B200_FAIL(B200_EINVAL, "conv_path must be 0, 1 or 2");
     if (m->opt_conv_path != (int)value) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_conv_path = (int)value;
+  } else if (k == "pdl") {
+    if (m->opt_pdl != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
+    m->opt_pdl = value ? 1 : 0;
   } else if (k == "pool_fusion") {
     if (m->opt_pool_fusion != (value ? 1 : 0)) { cudaStreamSynchronize(m->ctx->stream); m->plans.clear(); }
     m->opt_pool_fusion = value ? 1 : 0;
