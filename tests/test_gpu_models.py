@@ -257,6 +257,35 @@ def test_pool_fusion_matches_separate_launches(ctx, tmp_path, cin, squeeze, hw, 
     assert np.array_equal(eng(xs), fused), "tile walking direction must not change the bits"
 
 
+def test_pool_fusion_random_shapes(ctx, tmp_path):
+    """Seeded sweep over map sizes, channel counts, filter counts, batch sizes and zero padding at either end: the pool-fused
+    launch must give the bits of MaxPool + Conv (which the other tests pin against the oracle) whenever the planner fuses."""
+    from onnx_rusty_inference_engine_b200 import synth
+    from onnx_rusty_inference_engine_b200.inference_engine import Engine
+    rng = np.random.default_rng(20260)
+    fused_cases = 0
+    for case in range(14):
+        cin = int(rng.integers(2, 33)) * 4
+        squeeze = int(rng.integers(1, 17)) * 4
+        hw = int(rng.integers(9, 121))
+        pads = tuple(int(v) for v in rng.integers(0, 2, size=4))
+        batch = int(rng.integers(1, 4))
+        path = str(tmp_path / f"ps{case}.onnx")
+        with open(path, "wb") as f:
+            f.write(synth.build_pool_squeeze(cin, squeeze, hw, pads=pads, seed=case, tail=bool(case & 1)))
+        xs = synth.synthetic_batch(batch, chw=(cin, hw, hw), seed=100 + case, std=1.0)
+        if case % 3 == 0:
+            xs = -np.abs(xs)
+        eng = Engine(path, ctx=ctx)
+        fused = eng(xs)
+        kinds = [p["kind"] for p in eng.model.profile(batch, iters=1)]
+        eng.model.set_option("pool_fusion", 0)
+        separate = eng(xs)
+        assert np.array_equal(separate, fused), f"case {case}: cin={cin} squeeze={squeeze} hw={hw} pads={pads} batch={batch} kinds={kinds}"
+        fused_cases += "maxpool+conv_tc" in kinds
+    assert fused_cases >= 10, fused_cases
+
+
 def _assert_same_with_nonfinite(got, want, what):
     got = np.asarray(got); want = np.asarray(want)
     assert got.shape == want.shape
