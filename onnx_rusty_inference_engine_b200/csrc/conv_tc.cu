@@ -123,6 +123,7 @@ struct TcParams {
   int tile_rows;   // output pixels per tile: BM, or pool_rows * Wo in the pooled mode
   int pool_rows;   // pooled mode: a tile is pool_rows consecutive pooled rows of one image (MMA row = rho * Wo + j)
   int pool_tpi;    // pooled mode: tiles per image = ceil(Ho / pool_rows)
+  int half_a;      // 1: half-stage A ring (template HALFA): four {hi 16 | lo 16} stages + two accumulator stages (64 < BN <= 96, gather)
   int slab_pitch;  // bytes per row of an epilogue warp's slab (128 or 256)
   uint32_t zero;   // always 0; opaque to the compiler (builds data dependencies that must survive optimisation)
   int debug;       // B200_TC_DEBUG bit mask (timing experiments only): 1 skip weight TMA, 2 skip A loads, 4 skip stores, 16 skip MMAs, 32 skip the producers' tcgen05.st, 256 issue every MMA with N = 16
@@ -138,7 +139,7 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------ the kernel
 // NOPAD (gather layers whose taps all lie inside the image, e.g. conv1): a compile-time variant, so that the padded path's
 // masks and zero fill cost the no-padding producers neither registers nor instructions
-template <bool HAS_ADD, bool EPI16, bool NOPAD, bool POOL>
+template <bool HAS_ADD, bool EPI16, bool NOPAD, bool POOL, bool HALFA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapA, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -211,7 +212,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
   if (warp == TMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < p.S; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-      for (int s = 0; s < p.SA; ++s) { mbar_init(full_a(s), PROD_SET_WARPS); mbar_init(empty_a(s), 1); }
+      // HALFA: four half-stages, each filled by the four warps (one per lane quarter) of one (set, k half)
+      for (int s = 0; s < (HALFA ? 4 : p.SA); ++s) { mbar_init(full_a(s), HALFA ? PROD_SET_WARPS / 2 : PROD_SET_WARPS); mbar_init(empty_a(s), 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), NUM_EPI_WARPS); }
       for (int r = 0; r < p.R; ++r) { mbar_init(raw_full(r), 1); mbar_init(raw_empty(r), PROD_SET_WARPS); }
       for (int st = 0; st < 2; ++st)
@@ -419,6 +421,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
         for (int d = 0; d < PREFETCH; ++d) {
           const int it = base_i + d;
           if (it < my_items) {
+            if (HALFA) {
+              // half-stage ring (BN = 96 gather layers, so that TWO accumulator stages fit tensor memory): this warp's
+              // 16 k-floats of the k-block are a stage of their own -- {hi 16 | lo 16} columns at half-stage
+              // 2 * set + k half, always the same one, released by the MMA warp after two k-steps instead of four
+              const int hs = 2 * kpar + khalf;
+              mbar_wait(empty_a(hs), ph ^ 1u);
+              tc_fence_after();
+              if (!TC_DBG(32)) split_store(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a_col0 + hs * 32), v[d], 16u);
+              if (it + PREFETCH < my_items) issue(v[d]);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(full_a(hs));
+              ph ^= 1u;
+            } else {
             mbar_wait(empty_a(sa), ph ^ 1u);   // the MMAs that read this A stage have completed
             tc_fence_after();
             if (!TC_DBG(32)) split_store(t_a0 + (uint32_t)(sa * A_STAGE_COLS), v[d]);
@@ -429,6 +446,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
             if (lane == 0) mbar_arrive(full_a(sa));
             sa += NSETS;
             if (sa >= p.SA) { sa -= p.SA; ph ^= 1u; }
+            }
           }
         }
       }
@@ -557,6 +575,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant_
       const uint32_t d_corr = p.merged ? d_main : d_main + (uint32_t)p.BN;
       const uint32_t b_lo = (uint32_t)b_tile_bytes >> 4;   // B_lo follows B_hi in the stage (descriptor units of 16 bytes)
       for (int kb = 0; kb < p.nkb; ++kb) {
+        if (HALFA) {
+          // half-stage ring: `sa` counts the CTA's k-blocks modulo 2 (the producer set that filled this one), `pha` is the
+          // phase of that set's two half-stages.  Two k-steps per half-stage, each half released on its own.
+          mbar_wait(full_b(s), ph);
+          const int ksteps = (kb == p.nkb - 1) ? tail_ksteps : 4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int hs = 2 * sa + h;
+            mbar_wait(full_a(hs), pha);
+            tc_fence_after();
+            if (kb == 0 && h == 0) TC_TS(0, tc, 1);
+            if (leader && !TC_DBG(16)) {
+              const uint32_t ah = tmem_base + (uint32_t)(a_col0 + hs * 32), al = ah + 16u;
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int kk = 2 * h + k2;
+                if (kk < ksteps) {
+                  umma_tf32_ts(d_main, ah + 8u * k2, sw128_desc(lo + 2 * kk), idesc2, (kb | kk) != 0 ? 1u : 0u);
+                  umma_tf32_ts(d_corr, al + 8u * k2, sw128_desc(lo + 2 * kk), idesc, 1u);
+                }
+              }
+            }
+            __syncwarp();
+            if (leader) umma_commit(empty_a(hs));
+          }
+          if (leader) umma_commit(empty_b(s));
+          lo += lo_step;
+          if (++s == p.S) { s = 0; ph ^= 1u; lo = lo_first; }
+          if (++sa == 2) { sa = 0; pha ^= 1u; }
+          continue;
+        }
         mbar_wait(full_a(sa), pha);  // A stage written to tensor memory by all 8 producer warps
         mbar_wait(full_b(s), ph);
         tc_fence_after();
@@ -955,6 +1004,18 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   // measured: conv10 0.210 -> 0.175 ms, expand1x1 3-6 % faster; squeeze layers (BN <= 64, HBM-bound) and BN = 64
   // expands are better off with 8 + 16, like everything that gathers.
   static const int force_epi16 = [] { const char* e = getenv("B200_TC_EPI16"); return e ? atoi(e) : -1; }();   // experiments only
+  // Half-stage A ring: gather layers with 64 < BN <= 96 (conv1, fire6 / fire7 expand3x3).  Two {main | correction} stages
+  // (4 * BN columns) leave 128 columns for A: as two full stages that measured 5-13 % slower than one accumulator stage +
+  // four A stages (a set must refill its only stage while the MMA warp consumes the other set's); as FOUR half-stages of
+  // {hi 16 | lo 16} columns, one per (producer set, k half), a half is released after two k-steps and its four warps have
+  // three half-steps to refill it -- and the drain of tile i runs under the MMAs of tile i + 1.  Measured (tc_bench, one
+  // call): conv1 (7 k-blocks) 0.517 -> 0.497 ms, fire6 expand3x3 (14 k-blocks: the drain is 13 % of a tile) 0.130 -> 0.131:
+  // short reductions only.
+  static const int no_halfa = [] { const char* e = getenv("B200_TC_NO_HALFA"); return e ? atoi(e) : 0; }();   // experiments only
+  p.half_a = 0;
+  if (!no_halfa && !p.a_tma && !p.merged && p.nacc == 1 && force_nacc == 0 && 4 * p.BN + 4 * 32 <= 512 && p.nkb <= 8) {
+    p.half_a = 1; p.nacc = 2; p.SA = 4;
+  }
   bool epi16 = p.a_tma && p.BN > 64 && !a.pool;
   if (force_epi16 == 0) epi16 = false;
   if (force_epi16 == 1) epi16 = p.a_tma != 0 && !a.pool;
@@ -998,6 +1059,7 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   if (a.skip_m > 0 && a.skip_m % 16 == 0 && a.skip_m + 16 <= p.BN && p.n_tiles_n == 1 && !p.merged && a.skip_kb >= 1 && a.skip_kb < p.nkb) {
     p.skip_cols = a.skip_m; p.skip_kb = a.skip_kb;
   }
+  if (p.half_a) { p.skip_cols = 0; p.skip_kb = 0; }   // the half-stage MMA loop issues every column (the skipped ones are zeros anyway)
   p.nopad = (a.pt == 0 && a.pl == 0 && (long long)(a.Ho - 1) * a.sh + a.KH <= a.H && (long long)(a.Wo - 1) * a.sw + a.KW <= a.W) ? 1 : 0;
   p.magicC = a.C == 1 ? 0u : (uint32_t)(((1ull << 32) + a.C - 1) / a.C);
   p.magicKW = a.KW == 1 ? 0u : (uint32_t)(((1ull << 32) + a.KW - 1) / a.KW);
@@ -1009,14 +1071,18 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   B200_CUDA(cudaGetDevice(&dev));
   static int sm_count[64] = {0};
   if (dev < 64 && !attr_set[dev]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    B200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     B200_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
@@ -1049,10 +1115,12 @@ int launch_conv_tc(const ConvArgs& a, const TcWeights& w, cudaStream_t st) {
   }
   const bool nopad = p.nopad && !p.a_tma;
   void (*kernel)(const CUtensorMap, const CUtensorMap, const TcParams);
-  if (a.pool) kernel = a.chan_add ? conv_tc_kernel<true, false, false, true> : conv_tc_kernel<false, false, false, true>;
-  else if (epi16) kernel = a.chan_add ? conv_tc_kernel<true, true, false, false> : conv_tc_kernel<false, true, false, false>;
-  else if (nopad) kernel = a.chan_add ? conv_tc_kernel<true, false, true, false> : conv_tc_kernel<false, false, true, false>;
-  else kernel = a.chan_add ? conv_tc_kernel<true, false, false, false> : conv_tc_kernel<false, false, false, false>;
+  if (a.pool) kernel = a.chan_add ? conv_tc_kernel<true, false, false, true, false> : conv_tc_kernel<false, false, false, true, false>;
+  else if (epi16) kernel = a.chan_add ? conv_tc_kernel<true, true, false, false, false> : conv_tc_kernel<false, true, false, false, false>;
+  else if (p.half_a && nopad) kernel = a.chan_add ? conv_tc_kernel<true, false, true, false, true> : conv_tc_kernel<false, false, true, false, true>;
+  else if (p.half_a) kernel = a.chan_add ? conv_tc_kernel<true, false, false, false, true> : conv_tc_kernel<false, false, false, false, true>;
+  else if (nopad) kernel = a.chan_add ? conv_tc_kernel<true, false, true, false, false> : conv_tc_kernel<false, false, true, false, false>;
+  else kernel = a.chan_add ? conv_tc_kernel<true, false, false, false, false> : conv_tc_kernel<false, false, false, false, false>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid, 1, 1);

@@ -156,7 +156,7 @@ __device__ __forceinline__ float split_lo(float x, float hi) { return x - hi; }
 #define B200_SPLIT_RAW_HI 0
 #endif
 __device__ __forceinline__ float neg_trunc_tf32(float x) { return __uint_as_float((__float_as_uint(x) & 0xFFFFE000u) ^ 0x80000000u); }
-__device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[4]) {
+__device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[4], uint32_t lo_cols = 32u) {   // lo half lo_cols columns after hi
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const float4 a = x[2 * j], b = x[2 * j + 1];
@@ -167,7 +167,7 @@ __device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[
     const float2 a23 = __fadd2_rn(make_float2(a.z, a.w), make_float2(neg_trunc_tf32(a.z), neg_trunc_tf32(a.w)));
     const float2 b01 = __fadd2_rn(make_float2(b.x, b.y), make_float2(neg_trunc_tf32(b.x), neg_trunc_tf32(b.y)));
     const float2 b23 = __fadd2_rn(make_float2(b.z, b.w), make_float2(neg_trunc_tf32(b.z), neg_trunc_tf32(b.w)));
-    tmem_st_16x256b_x2(ta + 32u, a01.x, a01.y, b01.x, b01.y, a23.x, a23.y, b23.x, b23.y);
+    tmem_st_16x256b_x2(ta + lo_cols, a01.x, a01.y, b01.x, b01.y, a23.x, a23.y, b23.x, b23.y);
 #else
     float4 ah, bh, al, bl;
     ah.x = split_hi(a.x); ah.y = split_hi(a.y); ah.z = split_hi(a.z); ah.w = split_hi(a.w);
@@ -175,7 +175,7 @@ __device__ __forceinline__ void split_store(uint32_t t_stage, const float4 (&x)[
     tmem_st_16x256b_x2(ta, ah.x, ah.y, bh.x, bh.y, ah.z, ah.w, bh.z, bh.w);
     al.x = split_lo(a.x, ah.x); al.y = split_lo(a.y, ah.y); al.z = split_lo(a.z, ah.z); al.w = split_lo(a.w, ah.w);
     bl.x = split_lo(b.x, bh.x); bl.y = split_lo(b.y, bh.y); bl.z = split_lo(b.z, bh.z); bl.w = split_lo(b.w, bh.w);
-    tmem_st_16x256b_x2(ta + 32u, al.x, al.y, bl.x, bl.y, al.z, al.w, bl.z, bl.w);
+    tmem_st_16x256b_x2(ta + lo_cols, al.x, al.y, bl.x, bl.y, al.z, al.w, bl.z, bl.w);
 #endif
   }
 }

@@ -16,8 +16,8 @@ for r in rows:
     i = int(r["ID"])
     if i not in launches:
         full = r["Kernel Name"]
-        # conv_tc_kernel<HAS_ADD, EPI16, NOPAD, POOL>: the pool-fused instances are bandwidth launches, counted apart
-        pooled = re.search(r"conv_tc_kernel<(\(bool\))?\d, (\(bool\))?\d, (\(bool\))?\d, (\(bool\))?1>", full) is not None
+        # conv_tc_kernel<HAS_ADD, EPI16, NOPAD, POOL, HALFA>: the pool-fused instances are bandwidth launches, counted apart
+        pooled = re.search(r"conv_tc_kernel<(\(bool\))?\d, (\(bool\))?\d, (\(bool\))?\d, (\(bool\))?1, (\(bool\))?\d>", full) is not None
         launches[i] = {"kernel": full.split("(")[0][-48:] + ("POOL" if pooled else ""), "time": None, "dram_read": None, "dram_write": None}
         order.append(i)
     v = float(r["Metric Value"].replace(",", ""))
