@@ -103,10 +103,16 @@ def kernel_sources_sha() -> str:
     """sha256 over the sources that decide the launch list and the conv tiling: a committed ncu traffic figure is only
     quoted while it matches (it goes stale the moment the tiling changes)."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for name in KERNEL_SOURCES:
-        with open(os.path.join(ROOT, "onnx_rusty_inference_engine_b200", "csrc", name), "rb") as f:
-            h.update(f.read())
+        with open(os.path.join(ROOT, "onnx_rusty_inference_engine_b200", "csrc", name), "r", encoding="utf-8", errors="replace") as f:
+            text = f.read()
+        # code only: comments and blank space do not change what runs (no string literal in these files holds "//" or "/*")
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        text = "\n".join(ln.rstrip() for ln in text.splitlines() if ln.strip())
+        h.update(text.encode("utf-8"))
     return h.hexdigest()[:16]
 
 

@@ -6,9 +6,8 @@
 // in the producers) and issuing three tensor-core products per k-step: hi*hi into a main accumulator, lo*hi + hi*lo
 // into a separate correction accumulator (the tensor core truncates when it folds products into the fp32 accumulator;
 // keeping the 2^-11-times smaller terms apart costs no extra MMAs and removes two thirds of the truncation steps from
-// the main sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.  Short
-// reductions on wide tiles (BN > 64, K <= 288) use ONE merged accumulator instead, so that two accumulator stages fit
-// (launch_conv_tc, MERGED_MAX_K).
+// the main sum).  lo*lo is below fp32 rounding.  The two accumulators are added once, in the epilogue.  (Round 1 ran short
+// reductions on wide tiles with ONE merged accumulator so that two stages fit; retired: see MERGED_MAX_K.)
 //
 // GEMM view: D[P x M] = A[P x K] * W[M x K]^T, P = N*Ho*Wo output pixels, K = KH*KW*C ordered (r, s, c).
 //   UMMA tile 128 pixels (TMEM lanes) x BN <= 128 output channels (TMEM columns), k-block = 32 floats = 4 k-steps of
@@ -20,27 +19,34 @@
 //     puts float 4c+e of a 16-float group in TMEM column 2c+e (e < 2) or 8+2c+e-2 (e >= 2), so the weight
 //     preparation applies the same permutation to K inside every group of 16 (a contraction does not care).
 //   TMEM columns (512): [accumulator stages: {main | correction} x BN each][A stages: {hi 32 | lo 32} each].
-//     BN <= 64, or merged accumulator: two accumulator stages (the epilogue of tile i overlaps the main loop of tile
-//     i+1) + four A stages;  otherwise one accumulator stage, four A stages; the epilogue drains TMEM to a
-//     shared-memory slab first and releases the accumulator before it touches global memory.
+//     BN <= 64: two accumulator stages (the epilogue of tile i overlaps the main loop of tile i+1) + four A stages.
+//     64 < BN <= 96, gather, <= 8 k-blocks (HALFA, conv1): two accumulator stages + FOUR HALF-STAGES {hi 16 | lo 16},
+//     one per (producer set, k half), released after two k-steps each.
+//     Otherwise one accumulator stage + four A stages; the epilogue drains TMEM to a shared-memory slab first and
+//     releases the accumulator before it touches global memory.
 // One persistent CTA per SM (grid = min(tiles, SMs)), static round-robin tile schedule, 28 warps in one of two role
 // layouts (struct Roles); the default one:
 //   warps 0-7   epilogue: warps w, w+4 share TMEM lanes 32*(w%4).. and take the two halves of the tile's channels.
-//               Phase 1 drains: tcgen05.ld main + correction, add, + bias (+ channel add), Relu, row-per-thread into a
-//               private swizzled slab; then the accumulator stage is handed back.  Phase 2 writes the slab out with
-//               16-byte chunks, consecutive lanes along a row (complete 32-byte sectors of the channels-last rows).
+//               Phase 1 drains: tcgen05.ld main + correction, ONE add, row-per-thread into a private swizzled slab --
+//               nothing else, it sits between two tiles' MMAs -- then the accumulator stage is handed back.  Phase 2
+//               reads the slab back in 16-byte chunks, consecutive lanes along a row, applies bias (+ channel add) and
+//               Relu, and stores complete 32-byte sectors of the channels-last rows.
 //   warp 8      allocates TMEM, initialises mbarriers, issues the TMA loads of the weight tiles.
 //   warp 9      MMA issuer (uniform control flow, one elected lane, descriptors advanced by adds).
-//   warp 10     pointwise layers: TMA loads of raw fp32 A tiles into a shared-memory ring.
+//   warp 10     pointwise layers: TMA loads of raw fp32 A tiles into a shared-memory ring (POOL: of the 2R+1 input rows
+//               the tile's 3x3 / 2 max-pool windows touch, as 4-D boxes of the tensor before the pool).
 //   warps 10-11 gather layers: per-tile row decode ({offset, validity masks} of the tile's 128 im2col rows) into
 //               shared-memory tables, one tile ahead of the producer set each of them serves.
 //   warps 12-27 A producers, two sets of 8 that take alternate k-blocks: warp w owns TMEM lanes 32*(w%4).. (hardware
 //               rule) and the 64-byte half ((w-12)/4)%2 of each k-block row.  Gather mode: im2col rows straight from
 //               the channels-last activation (any stride / padding / tap; (r, s, offset) of a chunk from a per-CTA
-//               table; 2 k-blocks of loads in flight per thread).  Pointwise mode: read the TMA-fed raw tile.
+//               table; 2 k-blocks of loads in flight per thread).  Pointwise mode: read the TMA-fed raw tile (POOL:
+//               the maximum of the nine window chunks).
 // The second layout (pointwise layers with BN > 64): 16 epilogue warps, 8 converter warps.  The 896 threads start at 72
 // registers; setmaxnreg then gives the TMA/MMA warpgroup 40, the epilogue warpgroups 88 (80) and the converters 64.
 // Weights are split, permuted, padded and given a TMA descriptor ONCE per model (tc_prepare_weights).
+// Launches are programmatic dependent launches when the planner asks (ConvArgs::pdl): griddepcontrol.launch_dependents at
+// entry, griddepcontrol.wait between the prologue and the first access to activations.
 #include <cuda.h>
 
 #include <cstdlib>
