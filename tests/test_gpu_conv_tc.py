@@ -37,6 +37,10 @@ CASES = [
     (24, 16, 90, 90, 32, 1, 2, 0),         # 1x1 stride 2: ONE k-block per tile, so the sets take alternate tiles (380 tiles)
     (30, 8, 33, 33, 64, 3, 1, 1),          # three k-blocks (odd): a set's k-blocks alternate position from tile to tile
     (26, 4, 30, 30, 16, 3, 1, 0),          # no padding (mask-free path), two k-blocks, BN = 16, 160 tiles
+    # half-stage A ring (64 < BN <= 96, <= 8 k-blocks): two accumulator stages, four {hi 16 | lo 16} A half-stages
+    (20, 8, 33, 33, 96, 3, 1, 1),          # padded gather, three k-blocks (odd: a set's half-stages change tile position), 171 tiles
+    (30, 4, 40, 40, 80, 5, 1, 2),          # padded 5x5, K = 100 (four k-blocks, 4-float tail), BN = 80, 375 tiles
+    (40, 4, 61, 61, 96, 7, 2, 0),          # conv1 geometry, mask-free path, seven k-blocks, 245 tiles: several tiles per CTA
 ]
 
 
